@@ -1,0 +1,141 @@
+"""Generate golden vectors by running the REFERENCE's own code (dev container only).
+
+Usage (needs /root/reference, which does not exist on the GPU box):
+
+    python tools/make_golden_from_reference.py
+
+``import raglite`` fails offline (duckdb/sqlalchemy/litellm/rerankers/llama_cpp are not
+installed), but two pieces of the hot path are pure NumPy/SciPy once their imports resolve:
+
+* ``raglite/_embed.py``  -- ``embed_strings_with_late_chunking`` / ``_embed_string_batch``
+  (token counting, segmenting, largest-remainder split, mean pool, normalise, fp16 cast);
+* ``raglite/_query_adapter.py`` -- ``_optimize_query_target``.
+
+This script loads those two files *unmodified from where they lie* under a synthetic ``raglite``
+package whose heavy dependencies are replaced by stubs, and whose embedder is
+``tests/fake_llama.FakeLlama``.  Outputs go to ``tests/golden/*.npz`` (committed).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import json
+import sys
+import types
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference/src/raglite")
+sys.path.insert(0, str(REPO / "tests"))
+from fake_llama import FakeLlama, make_sentences  # noqa: E402
+
+GOLDEN = REPO / "tests" / "golden"
+
+
+class _Anything:
+    """Attribute sink: any attribute / call returns another sink (for unused ORM symbols)."""
+
+    def __getattr__(self, name):  # noqa: ANN001, ANN204
+        return _Anything()
+
+    def __call__(self, *a, **k):  # noqa: ANN002, ANN003, ANN204
+        return _Anything()
+
+
+def _stub(name: str, **attrs) -> types.ModuleType:  # noqa: ANN003
+    mod = types.ModuleType(name)
+    mod.__dict__.update(attrs)
+    mod.__getattr__ = lambda attr: _Anything()  # type: ignore[method-assign]
+    sys.modules[name] = mod
+    return mod
+
+
+def _load(name: str, path: Path) -> types.ModuleType:
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@dataclass(frozen=True)
+class _Config:
+    embedder: str = "llama-cpp-python/fake/fake.gguf@64"
+    embedder_normalize: bool = True
+    vector_search_distance_metric: str = "cosine"
+
+
+_CURRENT: dict[str, FakeLlama] = {}
+
+
+class _LlamaCppPythonLLM:
+    @staticmethod
+    def llm(model: str, **kwargs):  # noqa: ANN003, ANN205, ARG004
+        return _CURRENT["llm"]
+
+
+def install_reference_stubs() -> tuple[types.ModuleType, types.ModuleType]:
+    pkg = types.ModuleType("raglite")
+    pkg.__path__ = []  # a package, but never executes the reference's __init__ (it imports the world)
+    sys.modules["raglite"] = pkg
+    _stub("litellm", embedding=_Anything())
+    _stub("sqlalchemy", text=_Anything())
+    _stub("sqlalchemy.orm")
+    _stub("sqlalchemy.orm.attributes", flag_modified=_Anything())
+    _stub("sqlmodel", Session=_Anything(), col=_Anything(), select=_Anything())
+    _stub("raglite._config", RAGLiteConfig=_Config)
+    _stub("raglite._lazy_llama", LLAMA_POOLING_TYPE_NONE=0, Llama=FakeLlama)
+    _stub("raglite._litellm", LlamaCppPythonLLM=_LlamaCppPythonLLM)
+    _stub("raglite._typing", FloatMatrix=np.ndarray, FloatVector=np.ndarray, IntVector=np.ndarray)
+    _stub("raglite._database")
+    _stub("raglite._search", vector_search=_Anything())
+    embed = _load("raglite._embed", REF / "_embed.py")
+    qa = _load("raglite._query_adapter", REF / "_query_adapter.py")
+    return embed, qa
+
+
+def golden_pool(embed_mod: types.ModuleType) -> None:
+    cases = [
+        dict(name="pool_small", n_sent=9, n_ctx=64, dim=32, seed=1, normalize=True),
+        dict(name="pool_multi", n_sent=70, n_ctx=96, dim=48, seed=2, normalize=True),
+        dict(name="pool_nonorm", n_sent=33, n_ctx=80, dim=40, seed=3, normalize=False),
+        dict(name="pool_wide", n_sent=120, n_ctx=512, dim=384, seed=4, normalize=True),
+    ]
+    for c in cases:
+        llm = FakeLlama(n_ctx=c["n_ctx"], dim=c["dim"], seed=c["seed"])
+        _CURRENT["llm"] = llm
+        sentences = make_sentences(c["n_sent"], seed=c["seed"])
+        cfg = _Config(embedder_normalize=c["normalize"])
+        out = embed_mod.embed_strings_with_late_chunking(sentences, config=cfg)
+        simple = embed_mod._embed_string_batch(sentences[:7], config=cfg)  # noqa: SLF001
+        np.savez_compressed(
+            GOLDEN / f"{c['name']}.npz",
+            meta=np.frombuffer(json.dumps({**c, "sentences": sentences}).encode(), dtype=np.uint8),
+            late_chunking=out,
+            simple=simple,
+        )
+        print(c["name"], out.shape, out.dtype, simple.shape)
+
+
+def golden_adapter(qa_mod: types.ModuleType) -> None:
+    rng = np.random.default_rng(7)
+    arrays = {}
+    for i, (d, npos, nneg, dtype) in enumerate([(16, 2, 5, np.float16), (48, 3, 9, np.float32), (96, 1, 12, np.float16)]):
+        def unit(n):  # noqa: ANN001, ANN202
+            x = rng.standard_normal((n, d))
+            return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(dtype)
+        q, P, N = unit(1)[0], unit(npos), unit(nneg)
+        t = qa_mod._optimize_query_target(q, P, N, α=0.05)  # noqa: SLF001
+        arrays.update({f"q{i}": q, f"P{i}": P, f"N{i}": N, f"t{i}": t})
+    np.savez_compressed(GOLDEN / "adapter_target.npz", **arrays)
+    print("adapter_target", sorted(arrays))
+
+
+if __name__ == "__main__":
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    embed_mod, qa_mod = install_reference_stubs()
+    golden_pool(embed_mod)
+    golden_adapter(qa_mod)
