@@ -1,0 +1,163 @@
+/* raglite_b200 -- C-ABI of the B200-native RAGLite retrieval hot path.
+ *
+ * Every entry point takes plain device/host pointers, sizes and a CUDA stream handle
+ * (`void* stream` == cudaStream_t); there are no torch / C++ types in any signature.
+ * Return value: 0 on success, a negative RL_E* code on failure; rl_last_error() gives the
+ * message of the last failure on the calling thread.  No entry point allocates device memory:
+ * the caller passes a workspace sized by the matching *_workspace_bytes() query.  All calls are
+ * asynchronous on `stream` and re-entrant (no global mutable state), so several host threads may
+ * drive different streams concurrently (reference callers use thread pools: _rag.py:317,
+ * _eval.py:178).
+ *
+ * The reference (superlinear-ai/raglite @ 2069f8d) is pure Python and has no FFI; each entry point
+ * cites the Python code whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a
+ * RAGLite maintainer would add.
+ */
+#ifndef RAGLITE_B200_H_
+#define RAGLITE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_OK 0
+#define RL_EINVAL (-1)    /* bad argument (null pointer, unsupported size/metric, misalignment) */
+#define RL_ECUDA (-2)     /* a CUDA runtime call failed */
+#define RL_ENOSPACE (-3)  /* workspace too small */
+#define RL_EUNSUPPORTED (-4)
+
+/* Distance metric: RAGLiteConfig.vector_search_distance_metric (_config.py:69), rendered per
+ * dialect at _typing.py:110-134.  sim = 1 - dist (_search.py:72). */
+#define RL_METRIC_COSINE 0 /* dist = 1 - <e,q>/sqrt(|e|^2 |q|^2)  (array_cosine_distance)        */
+#define RL_METRIC_DOT 1    /* dist = -<e,q>                        (array_negative_inner_product) */
+#define RL_METRIC_L2 2     /* dist = |e - q|_2                     (array_distance)               */
+
+/* Scan kernel selection. */
+#define RL_ALGO_AUTO 0
+#define RL_ALGO_FP32 1    /* exact fp32 CUDA-core scan (any d) */
+#define RL_ALGO_TCGEN05 2 /* fp16-input tcgen05/TMEM coarse scan + exact rescoring (d % 4 == 0) */
+
+/* rl_maxsim_topk flags. */
+#define RL_FLAG_REUSE_THRESHOLDS 1u /* skip the sample pass; use thresholds left in the workspace */
+#define RL_FLAG_TIME_KERNELS 2u     /* record CUDA events around each stage (see rl_maxsim_kernel_times) */
+
+/* Per-query status bits written by rl_maxsim_topk. */
+#define RL_STATUS_CAND_OVERFLOW 1 /* candidate list overflowed: call again with REUSE_THRESHOLDS */
+#define RL_STATUS_TIE_OVERFLOW 2  /* > RL_MAX_SURVIVORS rows within the error band of the cut   */
+
+#define RL_MAX_SURVIVORS 4096
+
+int rl_version(void);
+const char* rl_last_error(void);
+
+/* Number of SMs etc. of the current device (diagnostics for bench.py). */
+int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* ---- Index build -------------------------------------------------------------------------
+ * Per-row statistics of the embedding matrix E[n_rows, d] (row stride ld floats): inv_norm[j] =
+ * 1/|e_j| (0 for a zero row), sq_norm[j] = |e_j|^2, and the global max row norm / max |element|
+ * (stats[0], stats[1]; device floats, must be zeroed by the caller) used to scale rows for the
+ * fp16 scan.  Replaces nothing in the reference (DuckDB recomputes norms per query inside
+ * array_cosine_distance); it is the device-side part of building the resident index from the
+ * chunk_embedding table (_database.py:403-430). */
+int rl_row_stats(const float* E, int64_t n_rows, int d, int64_t ld, float* inv_norm, float* sq_norm,
+                 float* stats, void* stream);
+
+/* row_chunk[j] = c for chunk_off[c] <= j < chunk_off[c+1]  (CSR -> per-row owner; the
+ * chunk_embedding.chunk_id column, _database.py:421). */
+int rl_chunk_row_map(const int64_t* chunk_off, int64_t n_chunks, int32_t* row_chunk, void* stream);
+
+/* ---- Query adapter apply: _search.py:58-62 -------------------------------------------------
+ * Q_out[b,:] = round_to(A @ Q_in[b,:]) with A[d,d] float64 row-major exactly as the reference
+ * stores it (_query_adapter.py:211), accumulated in float64; round_mode 0 = keep float32,
+ * 1 = round through float16 (the reference casts back to the query dtype, fp16 for string
+ * queries, _embed.py:140). */
+int rl_adapter_apply(const double* A, const float* Q_in, float* Q_out, int B, int d, int round_mode,
+                     void* stream);
+
+/* ---- MaxSim scan + top-k: _search.py:65-79, 143-153 -----------------------------------------
+ * One shard of the corpus, a batch of B queries.
+ *   E[n_rows,d] float32 row-major (ld = row stride in floats), inv_norm/sq_norm from
+ *   rl_row_stats, row_chunk from rl_chunk_row_map, chunk_base = global index of this shard's
+ *   first chunk, max_vecs_per_chunk = max CSR segment length, row_stats = stats from rl_row_stats.
+ *   row_allowed: optional uint8[n_rows] (metadata filter-first branch, _search.py:105-121), or NULL.
+ *   Q[B,d] float32 (already adapter-applied).
+ *   num_hits > 0: reference SQL semantics -- the num_hits vectors with smallest distance
+ *     (_search.py:75-79); hits are those vectors, ascending distance.
+ *   num_hits == 0: exact per-chunk MaxSim -- hits are the best k chunks.
+ * Outputs (H = num_hits ? num_hits : k):
+ *   hit_sim[B,H] float32 (sim = 1 - dist), hit_chunk[B,H] int64 global chunk index,
+ *   hit_count[B] int32, status[B] int32 (RL_STATUS_* bits).
+ * Feed the hit lists of all shards to rl_topk_merge for the GROUP BY / ORDER BY / LIMIT. */
+typedef struct rl_scan_params {
+  const float* E;
+  const float* inv_norm;
+  const float* sq_norm;
+  const int32_t* row_chunk;
+  const float* row_stats;
+  const uint8_t* row_allowed;
+  int64_t n_rows;
+  int64_t ld;
+  int64_t chunk_base;
+  int32_t d;
+  int32_t max_vecs_per_chunk;
+  const float* Q;
+  int32_t B;
+  int32_t metric;
+  int32_t k;
+  int32_t num_hits;
+  int32_t algo;
+  uint32_t flags;
+  int32_t sample_stride; /* 0 = auto */
+  int32_t cand_cap;      /* 0 = auto */
+} rl_scan_params;
+
+size_t rl_maxsim_workspace_bytes(const rl_scan_params* p);
+int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* hit_chunk, int32_t* hit_count,
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Counters of the last rl_maxsim_topk call on this workspace (device->host copy, synchronises the
+ * stream): kernel launches issued, and per-call totals of emitted candidates / survivors. */
+typedef struct rl_scan_stats {
+  int32_t launches;
+  int32_t sample_stride;
+  int32_t cand_cap;
+  int32_t algo;
+  int64_t n_sample_rows;
+  int64_t cand_total;
+  int64_t cand_max;
+  int64_t survivors_total;
+} rl_scan_stats;
+int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream);
+
+/* Device time in ms of the stages of the last rl_maxsim_topk call made with RL_FLAG_TIME_KERNELS on
+ * this workspace: ms[0] = prep, ms[1] = sample scan (dump), ms[2] = select, ms[3] = main scan (emit),
+ * ms[4] = finalize.  CUDA events are recorded on the launching stream; the call synchronises on the
+ * last one.  Diagnostics for bench.py's roofline figure. */
+int rl_maxsim_kernel_times(const void* workspace, float* ms);
+
+/* ---- Shard merge + GROUP BY chunk + top-k: _search.py:143-150 --------------------------------
+ * hit_*[R,B,H] are the per-shard outputs of rl_maxsim_topk (all-gathered).  num_hits > 0: keep
+ * the num_hits best vectors overall, group by chunk (max sim), order desc, limit k.  num_hits == 0:
+ * merge the per-shard chunk lists, limit k.  Outputs out_sim[B,k], out_chunk[B,k] (-1 padded),
+ * out_count[B]. */
+int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t* hit_count, int R,
+                  int B, int H, int num_hits, int k, float* out_sim, int64_t* out_chunk,
+                  int32_t* out_count, void* stream);
+
+/* ---- Late-chunking pool: _embed.py:129-140 (and the simple pool :154-164) ---------------------
+ * X[T,d] token embeddings (float32, row stride ld); sentence s averages rows
+ * [row_begin[s], row_end[s]) (host computes them with the largest-remainder rule, _embed.py:122-128;
+ * preamble sentences are simply not listed), then optional L2 normalisation (normalize: 0 = off,
+ * 1 = divide by the norm as _embed.py:139, 2 = eps-guarded as _embed.py:161-163) and a cast to
+ * float16 (out[S,d], IEEE binary16 bit patterns).  Accumulation is float64 like NumPy's. */
+int rl_segment_mean_pool(const float* X, int64_t ld, int d, const int32_t* row_begin,
+                         const int32_t* row_end, int S, int normalize, uint16_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAGLITE_B200_H_ */

@@ -1,0 +1,27 @@
+"""raglite_b200 -- B200-native (sm_100a) implementation of RAGLite's retrieval hot path.
+
+Drop-in surface (reference ``raglite/__init__.py`` names for this path): ``RAGLiteConfig``,
+``vector_search``, ``rerank_chunks``, ``embed_strings``; plus the device-resident ``CorpusIndex`` /
+``ShardedIndex`` that replace the database for this path and the batched ``vector_search_batch``.
+"""
+
+from ._config import RAGLiteConfig
+from ._embed import embed_strings, register_token_embedder
+from ._index import Chunk, CorpusIndex, get_index, merge_hits, register_index, unregister_index
+from ._search import rerank_chunks, retrieve_chunks, vector_search, vector_search_batch
+
+__all__ = [
+    "Chunk",
+    "CorpusIndex",
+    "RAGLiteConfig",
+    "embed_strings",
+    "get_index",
+    "merge_hits",
+    "register_index",
+    "register_token_embedder",
+    "rerank_chunks",
+    "retrieve_chunks",
+    "unregister_index",
+    "vector_search",
+    "vector_search_batch",
+]

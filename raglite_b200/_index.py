@@ -1,0 +1,271 @@
+"""Device-resident corpus index: the hot-path view of RAGLite's ``chunk_embedding`` table.
+
+Layout in HBM (one shard per GPU, rows of a chunk contiguous as the reference inserts them,
+``_insert.py:247-251``; variable vectors per chunk, ``_split_chunks.py:121``):
+
+    E          float32 [N, d] row-major      -- ``chunk_embedding.embedding`` (DuckDB FLOAT[d], _typing.py:187-198)
+    inv_norm   float32 [N]                   -- 1 / |e_j|   (rl_row_stats)
+    sq_norm    float32 [N]                   -- |e_j|^2
+    row_chunk  int32   [N]                   -- owner chunk of each row (``chunk_embedding.chunk_id``)
+    chunk_off  int64   [C + 1] (host)        -- CSR offsets
+    chunk_ids  list[str] (host)              -- ``chunk.id`` strings handed back to the caller
+
+The registry maps ``RAGLiteConfig.db_url`` to an index, which is how the drop-in ``vector_search``
+finds its corpus given only a config (the reference opens the database named by ``db_url``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from collections.abc import Sequence
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_METRIC, RL_STATUS_CAND_OVERFLOW, ScanParams, ScanStats, check
+from ._typing import ChunkId
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else int(t.data_ptr())
+
+
+@dataclass
+class Chunk:
+    """Minimal stand-in for ``raglite._database.Chunk`` (``_database.py:196-324``): what
+    ``rerank_chunks`` needs -- an id and the ``str(chunk)`` text the cross-encoder scores."""
+
+    id: ChunkId
+    document_id: str = ""
+    index: int = 0
+    headings: str = ""
+    body: str = ""
+    metadata_: dict[str, Any] = field(default_factory=dict)
+
+    @property
+    def front_matter(self) -> str:
+        meta = "\n".join(f"{k}: {self.metadata_.get(k)}" for k in ("filename", "url", "uri") if self.metadata_.get(k))
+        return f"---\n{meta}\n---" if meta else ""
+
+    @property
+    def content(self) -> str:
+        """Front matter, contextual headings and body (``_database.py:317-324``)."""
+        return f"{self.front_matter}\n\n{self.headings.strip()}\n\n{self.body.strip()}".strip()
+
+    def __str__(self) -> str:
+        return self.content
+
+    def __hash__(self) -> int:
+        return hash(self.id)
+
+
+@dataclass
+class ScanResult:
+    """Device-side output of one shard scan (inputs of ``rl_topk_merge``)."""
+
+    hit_sim: torch.Tensor    # [B, H] float32
+    hit_chunk: torch.Tensor  # [B, H] int64 (global chunk index)
+    hit_count: torch.Tensor  # [B] int32
+    status: torch.Tensor     # [B] int32
+    num_hits: int
+    k: int
+
+
+class CorpusIndex:
+    """One shard of the corpus, resident on one GPU."""
+
+    def __init__(  # noqa: PLR0913
+        self,
+        embeddings: torch.Tensor | np.ndarray,
+        chunk_offsets: np.ndarray | Sequence[int] | None = None,
+        *,
+        vecs_per_chunk: int | None = None,
+        chunk_ids: Sequence[ChunkId] | None = None,
+        chunk_base: int = 0,
+        chunks: Sequence[Chunk] | None = None,
+        chunk_metadata: Sequence[dict[str, Any]] | None = None,
+        device: torch.device | str | None = None,
+    ) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("raglite_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        E = torch.as_tensor(embeddings)
+        if E.ndim != 2:
+            raise ValueError("embeddings must be [n_rows, d]")
+        self.E = E.to(device=self.device, dtype=torch.float32).contiguous()
+        self.n_rows, self.d = int(self.E.shape[0]), int(self.E.shape[1])
+        if chunk_offsets is None:
+            v = 1 if vecs_per_chunk is None else int(vecs_per_chunk)
+            if self.n_rows % v:
+                raise ValueError("n_rows is not a multiple of vecs_per_chunk")
+            chunk_offsets = np.arange(0, self.n_rows + 1, v, dtype=np.int64)
+        self.chunk_off = np.ascontiguousarray(np.asarray(chunk_offsets, dtype=np.int64))
+        if self.chunk_off[0] != 0 or self.chunk_off[-1] != self.n_rows or np.any(np.diff(self.chunk_off) < 0):
+            raise ValueError("chunk_offsets must be a CSR offset array covering all rows")
+        self.n_chunks = len(self.chunk_off) - 1
+        counts = np.diff(self.chunk_off)
+        self.max_vecs = int(counts.max()) if self.n_chunks else 1
+        self.chunk_base = int(chunk_base)
+        self.chunk_ids = list(chunk_ids) if chunk_ids is not None else None
+        if self.chunk_ids is not None and len(self.chunk_ids) != self.n_chunks:
+            raise ValueError("chunk_ids must have one entry per chunk")
+        self.chunks = list(chunks) if chunks is not None else None
+        self.chunk_metadata = list(chunk_metadata) if chunk_metadata is not None else None
+        self.query_adapter: np.ndarray | None = None  # IndexMetadata["default"]["query_adapter"]
+        self._adapter_dev: torch.Tensor | None = None
+        self._ws: torch.Tensor | None = None
+        self._lock = threading.Lock()
+        self.last_params: ScanParams | None = None
+        with torch.cuda.device(self.device):
+            self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            self.sq_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+            self.row_chunk = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
+            off_dev = torch.from_numpy(self.chunk_off).to(self.device)
+            check(self.lib.rl_row_stats(_ptr(self.E), self.n_rows, self.d, self.d, _ptr(self.inv_norm),
+                                        _ptr(self.sq_norm), _ptr(self.stats), _stream()), "rl_row_stats")
+            check(self.lib.rl_chunk_row_map(_ptr(off_dev), self.n_chunks, _ptr(self.row_chunk), _stream()),
+                  "rl_chunk_row_map")
+            torch.cuda.current_stream().synchronize()
+
+    # ---- query adapter (IndexMetadata.get("default")["query_adapter"], _search.py:60) ------------
+    def set_query_adapter(self, A: np.ndarray | None) -> None:
+        if A is None:
+            self.query_adapter, self._adapter_dev = None, None
+            return
+        A = np.asarray(A, dtype=np.float64)
+        if A.shape != (self.d, self.d):
+            raise ValueError(f"query adapter must be [{self.d}, {self.d}]")
+        self.query_adapter = A
+        self._adapter_dev = torch.from_numpy(np.ascontiguousarray(A)).to(self.device)
+
+    def apply_adapter(self, Q: torch.Tensor, *, round_fp16: bool) -> torch.Tensor:
+        """``(A @ q).astype(q.dtype)`` for a batch (``_search.py:62``), float64 accumulate on device."""
+        if self._adapter_dev is None:
+            return Q
+        out = torch.empty_like(Q)
+        with torch.cuda.device(self.device):
+            check(self.lib.rl_adapter_apply(_ptr(self._adapter_dev), _ptr(Q), _ptr(out), Q.shape[0], self.d,
+                                            1 if round_fp16 else 0, _stream()), "rl_adapter_apply")
+        return out
+
+    # ---- scan ---------------------------------------------------------------------------------------
+    def _params(self, Q: torch.Tensor, k: int, num_hits: int, metric: str, algo: str,
+                row_allowed: torch.Tensor | None, flags: int, sample_stride: int, cand_cap: int) -> ScanParams:
+        p = ScanParams()
+        p.E, p.inv_norm, p.sq_norm = _ptr(self.E), _ptr(self.inv_norm), _ptr(self.sq_norm)
+        p.row_chunk, p.row_stats, p.row_allowed = _ptr(self.row_chunk), _ptr(self.stats), _ptr(row_allowed)
+        p.n_rows, p.ld, p.chunk_base = self.n_rows, self.d, self.chunk_base
+        p.d, p.max_vecs_per_chunk = self.d, max(1, self.max_vecs)
+        p.Q, p.B = _ptr(Q), int(Q.shape[0])
+        p.metric, p.k, p.num_hits, p.algo = RL_METRIC[metric], int(k), int(num_hits), RL_ALGO[algo]
+        p.flags, p.sample_stride, p.cand_cap = flags, sample_stride, cand_cap
+        return p
+
+    def scan(  # noqa: PLR0913
+        self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
+        row_allowed: torch.Tensor | None = None, flags: int = 0, sample_stride: int = 0, cand_cap: int = 0,
+        out: ScanResult | None = None,
+    ) -> ScanResult:
+        """Asynchronous shard scan on the current stream: Q is float32 ``[B, d]`` on this device."""
+        if Q.dtype != torch.float32 or Q.ndim != 2 or Q.shape[1] != self.d or not Q.is_contiguous():
+            raise ValueError(f"Q must be a contiguous float32 [B, {self.d}] tensor")
+        if metric not in RL_METRIC:
+            raise ValueError(f"Unsupported metric: {metric}")
+        B = int(Q.shape[0])
+        H = num_hits if num_hits > 0 else k
+        with self._lock, torch.cuda.device(self.device):
+            p = self._params(Q, k, num_hits, metric, algo, row_allowed, flags, sample_stride, cand_cap)
+            need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
+            if need == 0 and B > 0:
+                raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            if out is None:
+                out = ScanResult(
+                    torch.empty((B, H), dtype=torch.float32, device=self.device),
+                    torch.empty((B, H), dtype=torch.int64, device=self.device),
+                    torch.empty((B,), dtype=torch.int32, device=self.device),
+                    torch.empty((B,), dtype=torch.int32, device=self.device), num_hits, k)
+            check(self.lib.rl_maxsim_topk(C.byref(p), _ptr(out.hit_sim), _ptr(out.hit_chunk), _ptr(out.hit_count),
+                                          _ptr(out.status), _ptr(self._ws), self._ws.numel(), _stream()),
+                  "rl_maxsim_topk")
+            self.last_params = p
+        return out
+
+    def scan_stats(self) -> dict[str, int]:
+        """Counters of the last scan (synchronises)."""
+        if self.last_params is None or self._ws is None:
+            return {}
+        st = ScanStats()
+        with torch.cuda.device(self.device):
+            check(self.lib.rl_maxsim_stats(C.byref(self.last_params), _ptr(self._ws), C.byref(st), _stream()),
+                  "rl_maxsim_stats")
+        return {name: int(getattr(st, name)) for name, _ in ScanStats._fields_}
+
+    def kernel_times_ms(self) -> dict[str, float]:
+        """Stage times of the last scan made with ``flags=RL_FLAG_TIME_KERNELS`` (synchronises)."""
+        ms = (C.c_float * 5)()
+        check(self.lib.rl_maxsim_kernel_times(_ptr(self._ws), ms), "rl_maxsim_kernel_times")
+        return dict(zip(("prep", "sample_scan", "select", "main_scan", "finalize"), (float(x) for x in ms), strict=True))
+
+    def scan_checked(self, Q: torch.Tensor, **kw: Any) -> ScanResult:
+        """Scan, read the status back, and re-run with tightened thresholds while any query's
+        candidate list overflowed (rare: adversarial corpus order)."""
+        res = self.scan(Q, **kw)
+        for _ in range(4):
+            status = res.status.cpu()
+            if not bool((status & RL_STATUS_CAND_OVERFLOW).any()):
+                break
+            res = self.scan(Q, **{**kw, "flags": kw.get("flags", 0) | RL_FLAG_REUSE_THRESHOLDS}, out=res)
+        return res
+
+    def chunk_id_of(self, global_chunk: int) -> ChunkId:
+        local = int(global_chunk) - self.chunk_base
+        return self.chunk_ids[local] if self.chunk_ids is not None else str(int(global_chunk))
+
+
+def merge_hits(  # noqa: PLR0913
+    hit_sim: torch.Tensor, hit_chunk: torch.Tensor, hit_count: torch.Tensor, *, num_hits: int, k: int
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``rl_topk_merge`` over ``[R, B, H]`` gathered shard outputs -> ``(sim[B,k], chunk[B,k], count[B])``."""
+    lib = _lib.load()
+    if hit_sim.ndim == 2:
+        hit_sim, hit_chunk, hit_count = hit_sim[None], hit_chunk[None], hit_count[None]
+    R, B, H = (int(x) for x in hit_sim.shape)
+    dev = hit_sim.device
+    out_sim = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_chunk = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    hs, hc, hn = hit_sim.contiguous(), hit_chunk.contiguous(), hit_count.contiguous()
+    with torch.cuda.device(dev):
+        check(lib.rl_topk_merge(_ptr(hs), _ptr(hc), _ptr(hn), R, B, H, num_hits, k, _ptr(out_sim), _ptr(out_chunk),
+                                _ptr(out_count), _stream()), "rl_topk_merge")
+    return out_sim, out_chunk, out_count
+
+
+# ---- registry: RAGLiteConfig.db_url -> index ---------------------------------------------------------
+_REGISTRY: dict[str, Any] = {}
+
+
+def register_index(config_or_url: Any, index: Any) -> None:
+    """Attach a device-resident index to a ``RAGLiteConfig`` (keyed by ``db_url``)."""
+    _REGISTRY[str(getattr(config_or_url, "db_url", config_or_url))] = index
+
+
+def unregister_index(config_or_url: Any) -> None:
+    _REGISTRY.pop(str(getattr(config_or_url, "db_url", config_or_url)), None)
+
+
+def get_index(config: Any) -> Any | None:
+    return _REGISTRY.get(str(config.db_url))

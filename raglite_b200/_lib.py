@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI in include/raglite_b200.h.
+
+There is no CPU fallback: if the shared library cannot be loaded (or built), every entry point
+raises.  Device pointers are passed as integers (``tensor.data_ptr()``), the stream as the raw
+``cudaStream_t`` of ``torch.cuda.current_stream()``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+from . import _build
+
+RL_METRIC = {"cosine": 0, "dot": 1, "l2": 2}
+RL_ALGO = {"auto": 0, "fp32": 1, "tcgen05": 2}
+RL_FLAG_REUSE_THRESHOLDS = 1
+RL_FLAG_TIME_KERNELS = 2
+RL_STATUS_CAND_OVERFLOW = 1
+RL_STATUS_TIE_OVERFLOW = 2
+RL_MAX_SURVIVORS = 4096
+
+EXPORTS = [
+    "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_chunk_row_map", "rl_adapter_apply",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_topk_merge",
+    "rl_segment_mean_pool",
+]
+
+
+class ScanParams(C.Structure):
+    _fields_ = [
+        ("E", C.c_void_p), ("inv_norm", C.c_void_p), ("sq_norm", C.c_void_p), ("row_chunk", C.c_void_p),
+        ("row_stats", C.c_void_p), ("row_allowed", C.c_void_p),
+        ("n_rows", C.c_int64), ("ld", C.c_int64), ("chunk_base", C.c_int64),
+        ("d", C.c_int32), ("max_vecs_per_chunk", C.c_int32),
+        ("Q", C.c_void_p),
+        ("B", C.c_int32), ("metric", C.c_int32), ("k", C.c_int32), ("num_hits", C.c_int32), ("algo", C.c_int32),
+        ("flags", C.c_uint32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32),
+    ]
+
+
+class ScanStats(C.Structure):
+    _fields_ = [
+        ("launches", C.c_int32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32), ("algo", C.c_int32),
+        ("n_sample_rows", C.c_int64), ("cand_total", C.c_int64), ("cand_max", C.c_int64),
+        ("survivors_total", C.c_int64),
+    ]
+
+
+_lock = threading.Lock()
+_lib: C.CDLL | None = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.rl_version.restype = C.c_int
+    lib.rl_last_error.restype = C.c_char_p
+    lib.rl_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    lib.rl_row_stats.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp]
+    lib.rl_chunk_row_map.argtypes = [vp, i64, vp, vp]
+    lib.rl_adapter_apply.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    lib.rl_maxsim_workspace_bytes.argtypes = [C.POINTER(ScanParams)]
+    lib.rl_maxsim_workspace_bytes.restype = C.c_size_t
+    lib.rl_maxsim_topk.argtypes = [C.POINTER(ScanParams), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.rl_maxsim_stats.argtypes = [C.POINTER(ScanParams), vp, C.POINTER(ScanStats), vp]
+    lib.rl_maxsim_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.rl_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.rl_segment_mean_pool.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]
+    for name in EXPORTS:
+        if name not in ("rl_last_error", "rl_maxsim_workspace_bytes"):
+            getattr(lib, name).restype = C.c_int
+
+
+def load(*, build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if needed) the CUDA library.  Raises if that is impossible."""
+    global _lib  # noqa: PLW0603
+    with _lock:
+        if _lib is None:
+            path = _build.LIB_PATH
+            if build_if_missing and _build.is_stale():
+                path = _build.build()
+            if not path.exists():
+                raise RuntimeError(f"{path} is missing and could not be built; raglite_b200 has no CPU fallback")
+            lib = C.CDLL(str(path))
+            _declare(lib)
+            _lib = lib
+        return _lib
+
+
+class RagliteB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rl_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RagliteB200Error(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,186 @@
+"""Drop-in ``vector_search`` / ``rerank_chunks`` over the device-resident index.
+
+Signatures follow the reference (``raglite/_search.py:36-43`` and ``:364-366``); the arithmetic that
+the reference delegates to DuckDB SQL runs in the CUDA library instead.  ``vector_search_batch`` is
+the batched entry the benchmark configs use (the reference API is single-query, ``_search.py:54-56``).
+"""
+
+from __future__ import annotations
+
+import contextlib
+from collections.abc import Sequence
+from typing import Any
+
+import numpy as np
+import torch
+
+from ._config import RAGLiteConfig
+from ._index import Chunk, CorpusIndex, get_index, merge_hits
+from ._typing import ChunkId, FloatVector, MetadataFilter
+
+REFERENCE_CHUNK_MAX_SIZE = 2048  # RAGLiteConfig.chunk_max_size class default (_config.py:67)
+
+
+def num_hits_rule(num_results: int, oversample: int, chunk_max_size: int) -> int:
+    """``_search.py:66-67``."""
+    corrected_oversample = oversample * chunk_max_size / REFERENCE_CHUNK_MAX_SIZE
+    return round(corrected_oversample) * max(num_results, 10)
+
+
+def _adapt_metadata(metadata_filter: MetadataFilter | None) -> dict[str, list[Any]] | None:
+    """Normalise filter values to lists (``_database.py:51-55``)."""
+    if not metadata_filter:
+        return None
+    return {k: (list(v) if isinstance(v, (list, tuple)) else [v]) for k, v in metadata_filter.items()}
+
+
+def _allowed_rows(index: Any, metadata_filter: dict[str, list[Any]] | None) -> torch.Tensor | None:
+    """Filter-first branch (``_search.py:105-121``): rows whose chunk metadata contains every
+    requested value (JSON containment on list-valued metadata)."""
+    if not metadata_filter:
+        return None
+    local: CorpusIndex = getattr(index, "local", index)
+    if local.chunk_metadata is None:
+        raise ValueError("metadata_filter given but the index holds no chunk metadata")
+    ok = np.zeros(local.n_chunks, dtype=bool)
+    for c, meta in enumerate(local.chunk_metadata):
+        good = True
+        for key, wanted in metadata_filter.items():
+            have = meta.get(key)
+            have = have if isinstance(have, (list, tuple)) else [have]
+            if not all(w in have for w in wanted):
+                good = False
+                break
+        ok[c] = good
+    rows = np.repeat(ok, np.diff(local.chunk_off)).astype(np.uint8)
+    return torch.from_numpy(rows).to(local.device)
+
+
+def vector_search_batch(  # noqa: PLR0913
+    queries: np.ndarray | torch.Tensor,
+    *,
+    num_results: int = 3,
+    oversample: int = 4,
+    metadata_filter: MetadataFilter | None = None,
+    config: RAGLiteConfig | None = None,
+    index: Any | None = None,
+    exact_maxsim: bool = False,
+    algo: str = "auto",
+    queries_are_fp16: bool = False,
+) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Batched ``vector_search``: ``queries`` is ``[B, d]`` (host or device).
+
+    Returns host arrays ``(chunk_index[B, k] int64 (-1 padded), sim[B, k] float32, count[B])``.
+    ``exact_maxsim=True`` ranks by exact per-chunk MaxSim instead of the reference's
+    top-``num_hits``-vectors semantics.
+    """
+    config = config or RAGLiteConfig()
+    index = index if index is not None else get_index(config)
+    if index is None:
+        raise ValueError(f"No index registered for db_url={config.db_url!r}; use raglite_b200.register_index")
+    local: CorpusIndex = getattr(index, "local", index)
+    Q = torch.as_tensor(queries)
+    queries_are_fp16 = queries_are_fp16 or Q.dtype == torch.float16
+    Q = Q.to(device=local.device, dtype=torch.float32, non_blocking=True).contiguous()
+    if Q.ndim != 2:
+        raise ValueError("queries must be [B, d]")
+    k = int(num_results)
+    B = int(Q.shape[0])
+    if local.n_chunks == 0 and not hasattr(index, "search_device"):
+        return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
+    if config.vector_search_query_adapter and local.query_adapter is not None:
+        Q = local.apply_adapter(Q, round_fp16=queries_are_fp16)
+    num_hits = 0 if exact_maxsim else num_hits_rule(k, oversample, config.chunk_max_size)
+    if not exact_maxsim and num_hits == 0:  # round(oversample * size / 2048) == 0 -> LIMIT 0
+        return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
+    allowed = _allowed_rows(index, _adapt_metadata(metadata_filter))
+    metric = config.vector_search_distance_metric
+    if hasattr(index, "search_device"):  # sharded across ranks
+        sim, chunk, count = index.search_device(Q, k=k, num_hits=num_hits, metric=metric, algo=algo,
+                                                row_allowed=allowed, checked=True)
+    else:
+        res = local.scan_checked(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=allowed)
+        sim, chunk, count = merge_hits(res.hit_sim, res.hit_chunk, res.hit_count, num_hits=num_hits, k=k)
+    return chunk.cpu().numpy(), sim.cpu().numpy(), count.cpu().numpy()
+
+
+def vector_search(
+    query: str | FloatVector,
+    *,
+    num_results: int = 3,
+    oversample: int = 4,
+    metadata_filter: MetadataFilter | None = None,
+    config: RAGLiteConfig | None = None,
+) -> tuple[list[ChunkId], list[float]]:
+    """Search chunks by multi-vector similarity -- drop-in for ``raglite.vector_search``
+    (``_search.py:36-153``): embed / ravel the query, apply the query adapter, keep the
+    ``num_hits`` nearest vectors, group by chunk with ``max(sim)``, return the best ``num_results``."""
+    config = config or RAGLiteConfig()
+    index = get_index(config)
+    if index is None:
+        raise ValueError(f"No index registered for db_url={config.db_url!r}; use raglite_b200.register_index")
+    if config.self_query and isinstance(query, str):
+        raise NotImplementedError("self_query needs an LLM and is outside the accelerated hot path")
+    if isinstance(query, str):
+        from ._embed import embed_strings
+
+        q = embed_strings([query], config=config)[0, :]
+    else:
+        q = np.ravel(query)
+    local: CorpusIndex = getattr(index, "local", index)
+    ids, sims, counts = vector_search_batch(
+        q[None, :], num_results=num_results, oversample=oversample, metadata_filter=metadata_filter,
+        config=config, index=index, queries_are_fp16=(q.dtype == np.float16),
+    )
+    n = int(counts[0])
+    owner = index if hasattr(index, "chunk_id_of") else local
+    return [owner.chunk_id_of(int(c)) for c in ids[0, :n]], [float(s) for s in sims[0, :n]]
+
+
+def retrieve_chunks(chunk_ids: Sequence[ChunkId], *, config: RAGLiteConfig | None = None) -> list[Chunk]:
+    """``_search.py:283-299`` over the registered index's chunk table (order follows ``chunk_ids``)."""
+    config = config or RAGLiteConfig()
+    if not chunk_ids:
+        return []
+    index = get_index(config)
+    local = getattr(index, "local", index) if index is not None else None
+    if local is None or local.chunks is None:
+        raise ValueError("The registered index holds no chunk texts")
+    by_id = {c.id: c for c in local.chunks}
+    return [by_id[cid] for cid in chunk_ids if cid in by_id]
+
+
+def rerank_chunks(
+    query: str, chunk_ids: list[ChunkId] | list[Chunk], *, config: RAGLiteConfig | None = None
+) -> list[Chunk]:
+    """Rerank chunks by cross-encoder relevance -- drop-in for ``raglite.rerank_chunks``
+    (``_search.py:364-397``): same early exits, language routing and ``.rank(query=, docs=)`` contract."""
+    config = config or RAGLiteConfig()
+    chunks: list[Chunk] = (
+        retrieve_chunks(chunk_ids, config=config)  # type: ignore[arg-type]
+        if all(isinstance(c, ChunkId) for c in chunk_ids)
+        else list(chunk_ids)  # type: ignore[arg-type]
+    )
+    if not config.reranker or not chunks:
+        return chunks
+    if isinstance(config.reranker, dict):
+        langs: set[str] = set()
+        try:  # the reference detects languages with langdetect (_search.py:381-383); optional here
+            from langdetect import LangDetectException, detect  # type: ignore[import-not-found]
+
+            with contextlib.suppress(LangDetectException):
+                langs = {detect(str(chunk)) for chunk in chunks}
+                langs.add(detect(query))
+        except ModuleNotFoundError:
+            langs = set()
+        rerankers = config.reranker
+        if len(langs) == 1 and (lang := next(iter(langs))) in rerankers:
+            reranker = rerankers[lang]
+        else:
+            reranker = rerankers.get("other")
+    else:
+        reranker = config.reranker
+    if reranker:
+        results = reranker.rank(query=query, docs=[str(chunk) for chunk in chunks])
+        chunks = [chunks[result.doc_id] for result in results.results]
+    return chunks

@@ -1,0 +1,316 @@
+// C-ABI entry points of libraglite_b200 (see include/raglite_b200.h).
+#include <cmath>
+#include <cstdarg>
+#include <map>
+#include <mutex>
+
+#include "scan_common.cuh"
+#include "scan_tcgen05.cuh"
+#include "select_finalize.cuh"
+
+namespace rl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Stage timing events, keyed by workspace pointer (only touched when RL_FLAG_TIME_KERNELS is set).
+constexpr int kNumStageEvents = 6;
+struct StageEvents {
+  cudaEvent_t ev[kNumStageEvents];
+  bool valid = false;
+};
+static std::mutex g_ev_mutex;
+static std::map<const void*, StageEvents> g_events;
+
+static StageEvents* stage_events_for(const void* ws) {
+  std::lock_guard<std::mutex> lock(g_ev_mutex);
+  StageEvents& se = g_events[ws];
+  if (!se.valid) {
+    for (int i = 0; i < kNumStageEvents; ++i)
+      if (cudaEventCreate(&se.ev[i]) != cudaSuccess) return nullptr;
+    se.valid = true;
+  }
+  return &se;
+}
+
+static int floor_pow2(double x) {
+  int p = 1;
+  while ((double)(p * 2) <= x) p *= 2;
+  return p;
+}
+
+int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
+  (void)sm_count;
+  RL_REQUIRE(p != nullptr, RL_EINVAL, "null params");
+  RL_REQUIRE(p->n_rows >= 0 && p->n_rows < (1ll << 31) - kBlockRows, RL_EINVAL, "n_rows out of range");
+  RL_REQUIRE(p->d > 0 && p->d <= 16384 && p->ld >= p->d, RL_EINVAL, "bad d / ld");
+  RL_REQUIRE(p->B >= 0 && p->B <= 65535, RL_EINVAL, "bad B");
+  RL_REQUIRE(p->k > 0, RL_EINVAL, "k must be positive");
+  RL_REQUIRE(p->num_hits >= 0, RL_EINVAL, "num_hits must be >= 0");
+  RL_REQUIRE(p->metric >= RL_METRIC_COSINE && p->metric <= RL_METRIC_L2, RL_EINVAL, "unknown metric %d", p->metric);
+  RL_REQUIRE(p->max_vecs_per_chunk >= 1, RL_EINVAL, "max_vecs_per_chunk must be >= 1");
+  memset(L, 0, sizeof(*L));
+  L->mode_sql = p->num_hits > 0;
+  L->H = L->mode_sql ? p->num_hits : p->k;
+  const int64_t sel_final = L->mode_sql ? p->num_hits : (int64_t)(p->k - 1) * p->max_vecs_per_chunk + 1;
+  RL_REQUIRE(sel_final + sel_final / 4 <= RL_MAX_SURVIVORS, RL_EUNSUPPORTED,
+             "selection size %lld exceeds the %d-survivor finalize window (k=%d num_hits=%d max_vecs=%d)",
+             (long long)sel_final, RL_MAX_SURVIVORS, p->k, p->num_hits, p->max_vecs_per_chunk);
+  L->sel_k = L->mode_sql ? p->num_hits : p->k;  // order statistic searched in the sample
+  L->n_blocks = (p->n_rows + kBlockRows - 1) / kBlockRows;
+
+  int algo = p->algo;
+  const bool tc_ok = tcgen05_supported(p);
+  if (algo == RL_ALGO_AUTO) algo = tc_ok ? RL_ALGO_TCGEN05 : RL_ALGO_FP32;
+  RL_REQUIRE(algo == RL_ALGO_FP32 || algo == RL_ALGO_TCGEN05, RL_EINVAL, "unknown algo %d", p->algo);
+  RL_REQUIRE(algo != RL_ALGO_TCGEN05 || tc_ok, RL_EUNSUPPORTED,
+             "RL_ALGO_TCGEN05 needs d %% 4 == 0, ld %% 4 == 0, 16-byte aligned E and a supported metric");
+  L->algo = algo;
+
+  int S = p->sample_stride;
+  if (S <= 0) {
+    // Balance the cost of dumping a 1/S sample (B floats per sampled row) against the candidates
+    // the main pass then emits (~ sel_k * S per query, 8 bytes each plus select passes).
+    const double rows_per_sel = L->mode_sql ? 1.0 : (double)p->max_vecs_per_chunk;
+    const double f = std::sqrt((double)L->sel_k * rows_per_sel * 16.0 / ((double)(p->n_rows > 0 ? p->n_rows : 1) * 4.0));
+    S = floor_pow2(f > 0 ? 1.0 / f : 1.0);
+    if (S > 256) S = 256;
+    while (S > 1 && (L->n_blocks / S) * kBlockRows < 8 * (int64_t)(L->sel_k * rows_per_sel)) S /= 2;
+    if (L->n_blocks < 64) S = 1;
+  }
+  if (S < 1) S = 1;
+  L->S = S;
+  L->n_sample_blocks = (L->n_blocks + S - 1) / S;
+  L->n_main_blocks = L->n_blocks - L->n_sample_blocks;
+  L->n_sample_rows = L->n_sample_blocks * kBlockRows;
+
+  int64_t cap = p->cand_cap;
+  if (cap <= 0) {
+    cap = 4 * sel_final * S + 1024;
+    if (cap > p->n_rows + 1024) cap = p->n_rows + 1024;
+  }
+  if (cap < 256) cap = 256;
+  RL_REQUIRE(cap < (1ll << 30), RL_EINVAL, "cand_cap too large");
+  L->cap = (int)cap;
+
+  L->d_pad = (p->d + 63) / 64 * 64;
+  L->b_pad = (p->B + 15) / 16 * 16;
+  const size_t B = (size_t)(p->B > 0 ? p->B : 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  L->off_hdr = take(sizeof(Header));
+  L->off_cnt = take(B * 4);
+  L->off_thr = take(B * 4);
+  L->off_thr_out = take(B * 4);
+  L->off_eps = take(B * 4);
+  L->off_qinv = take(B * 4);
+  L->off_qsq = take(B * 8);
+  L->off_qscale = take(B * 4);
+  L->off_nsurv = take(B * 4);
+  L->off_qimg = take(algo == RL_ALGO_TCGEN05 ? tcgen05_qimg_bytes(p->B, p->d) : 0);
+  L->off_dump = take(B * (size_t)L->n_sample_rows * 4);
+  L->off_cand = take(B * (size_t)L->cap * sizeof(Cand));
+  L->total = off;
+  return RL_OK;
+}
+
+static int device_sm_count(int* out) {
+  int dev = 0;
+  RL_CUDA_CHECK(cudaGetDevice(&dev));
+  RL_CUDA_CHECK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return RL_OK;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" int rl_version(void) { return 100; }
+extern "C" const char* rl_last_error(void) { return g_err; }
+
+extern "C" int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
+  int dev = 0;
+  RL_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  RL_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (l2_bytes) *l2_bytes = (size_t)prop.l2CacheSize;
+  return RL_OK;
+}
+
+extern "C" size_t rl_maxsim_workspace_bytes(const rl_scan_params* p) {
+  Layout L;
+  if (make_layout(p, 148, &L) != RL_OK) return 0;
+  return L.total;
+}
+
+extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* hit_chunk, int32_t* hit_count,
+                              int32_t* status, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != RL_OK) return rc;
+  Layout L;
+  rc = make_layout(p, sms, &L);
+  if (rc != RL_OK) return rc;
+  if (p->B == 0) return RL_OK;
+  RL_REQUIRE(hit_sim && hit_chunk && hit_count && status && p->Q, RL_EINVAL, "rl_maxsim_topk: null pointer");
+  if (p->n_rows == 0) {  // empty shard: no hits (reference: empty database -> ([], []), tests/test_search.py:76-85)
+    RL_CUDA_CHECK(cudaMemsetAsync(hit_count, 0, (size_t)p->B * 4, stream));
+    RL_CUDA_CHECK(cudaMemsetAsync(status, 0, (size_t)p->B * 4, stream));
+    RL_CUDA_CHECK(cudaMemsetAsync(hit_chunk, 0xFF, (size_t)p->B * L.H * 8, stream));
+    RL_CUDA_CHECK(cudaMemsetAsync(hit_sim, 0xFF, (size_t)p->B * L.H * 4, stream));
+    return RL_OK;
+  }
+  RL_REQUIRE(p->E && p->inv_norm && p->sq_norm && p->row_chunk, RL_EINVAL, "rl_maxsim_topk: null index pointer");
+  RL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, RL_ENOSPACE,
+             "rl_maxsim_topk: workspace %zu < required %zu", workspace_bytes, L.total);
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, RL_EINVAL, "workspace must be 256-byte aligned");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  Header* hdr = reinterpret_cast<Header*>(ws + L.off_hdr);
+  int32_t* cand_cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+  float* thr = reinterpret_cast<float*>(ws + L.off_thr);
+  float* thr_out = reinterpret_cast<float*>(ws + L.off_thr_out);
+  float* eps = reinterpret_cast<float*>(ws + L.off_eps);
+  float* q_inv = reinterpret_cast<float*>(ws + L.off_qinv);
+  double* q_sq = reinterpret_cast<double*>(ws + L.off_qsq);
+  float* q_scale = reinterpret_cast<float*>(ws + L.off_qscale);
+  int32_t* n_surv = reinterpret_cast<int32_t*>(ws + L.off_nsurv);
+  void* qimg = ws + L.off_qimg;
+  float* dump = reinterpret_cast<float*>(ws + L.off_dump);
+  Cand* cand = reinterpret_cast<Cand*>(ws + L.off_cand);
+  const bool reuse = (p->flags & RL_FLAG_REUSE_THRESHOLDS) != 0;
+  int launches = 0;
+  StageEvents* se = (p->flags & RL_FLAG_TIME_KERNELS) ? stage_events_for(workspace) : nullptr;
+  auto mark = [&](int i) { if (se) cudaEventRecord(se->ev[i], stream); };
+  mark(0);
+
+  RL_CUDA_CHECK(cudaMemsetAsync(cand_cnt, 0, (size_t)p->B * 4, stream));
+  rc = launch_query_prep(p->Q, p->B, p->d, p->metric, L.algo, p->row_stats, q_sq, q_inv, eps, stream);
+  if (rc != RL_OK) return rc;
+  ++launches;
+  if (L.algo == RL_ALGO_TCGEN05) {
+    rc = tcgen05_prepare_queries(p, q_inv, q_scale, qimg, stream);
+    if (rc != RL_OK) return rc;
+    ++launches;
+  }
+
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.E = p->E; a.inv_norm = p->inv_norm; a.sq_norm = p->sq_norm; a.row_allowed = p->row_allowed;
+  a.Q = p->Q; a.q_inv_norm = q_inv; a.thr = thr; a.dump = dump; a.cand = cand; a.cand_cnt = cand_cnt;
+  a.n_rows = p->n_rows; a.ld = p->ld; a.n_sample_rows = L.n_sample_rows;
+  a.d = p->d; a.B = p->B; a.metric = p->metric; a.S = L.S; a.cap = L.cap;
+
+  auto scan = [&](int dump_mode, int64_t n_mode_blocks) -> int {
+    if (n_mode_blocks == 0) return RL_OK;
+    a.dump_mode = dump_mode;
+    a.n_mode_blocks = n_mode_blocks;
+    ++launches;
+    if (L.algo == RL_ALGO_TCGEN05) return launch_scan_tcgen05(a, p, q_scale, qimg, sms, stream);
+    return launch_scan_fp32(a, stream);
+  };
+
+  mark(1);
+  if (!reuse) {
+    rc = scan(1, L.n_sample_blocks);
+    if (rc != RL_OK) return rc;
+  } else {
+    RL_CUDA_CHECK(cudaMemcpyAsync(thr, thr_out, (size_t)p->B * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  mark(2);
+  SelectArgs s;
+  s.dump = dump; s.row_chunk = p->row_chunk; s.eps = eps; s.thr = thr; s.cand = cand; s.cand_cnt = cand_cnt;
+  s.n_sample_rows = L.n_sample_rows; s.n_rows = p->n_rows; s.S = L.S; s.cap = L.cap; s.mode_sql = L.mode_sql;
+  s.sel_k = L.sel_k; s.reuse_thr = reuse ? 1 : 0;
+  rc = launch_select(s, p->B, stream);
+  if (rc != RL_OK) return rc;
+  ++launches;
+  mark(3);
+  rc = scan(0, L.n_main_blocks);
+  if (rc != RL_OK) return rc;
+  mark(4);
+
+  FinalizeArgs f;
+  f.E = p->E; f.row_chunk = p->row_chunk; f.Q = p->Q; f.q_sq = q_sq; f.eps = eps; f.cand = cand; f.cand_cnt = cand_cnt;
+  f.thr_out = thr_out; f.hit_sim = hit_sim; f.hit_chunk = hit_chunk; f.hit_count = hit_count; f.status = status;
+  f.n_surv = n_surv; f.header = hdr; f.ld = p->ld; f.chunk_base = p->chunk_base; f.n_sample_rows = L.n_sample_rows;
+  f.d = p->d; f.metric = p->metric; f.cap = L.cap; f.mode_sql = L.mode_sql;
+  f.sel_k = L.mode_sql ? p->num_hits : (p->k - 1) * p->max_vecs_per_chunk + 1;
+  f.H = L.H; f.launches = launches + 1; f.S = L.S; f.algo = L.algo;
+  rc = launch_finalize(f, p->B, stream);
+  mark(5);
+  return rc;
+}
+
+extern "C" int rl_maxsim_kernel_times(const void* workspace, float* ms) {
+  RL_REQUIRE(workspace && ms, RL_EINVAL, "rl_maxsim_kernel_times: null pointer");
+  StageEvents se;
+  {
+    std::lock_guard<std::mutex> lock(g_ev_mutex);
+    auto it = g_events.find(workspace);
+    RL_REQUIRE(it != g_events.end() && it->second.valid, RL_EINVAL,
+               "rl_maxsim_kernel_times: no timed call on this workspace");
+    se = it->second;
+  }
+  RL_CUDA_CHECK(cudaEventSynchronize(se.ev[kNumStageEvents - 1]));
+  for (int i = 0; i + 1 < kNumStageEvents; ++i) RL_CUDA_CHECK(cudaEventElapsedTime(&ms[i], se.ev[i], se.ev[i + 1]));
+  return RL_OK;
+}
+
+extern "C" int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RL_REQUIRE(p && workspace && out, RL_EINVAL, "rl_maxsim_stats: null pointer");
+  Layout L;
+  int rc = make_layout(p, 148, &L);
+  if (rc != RL_OK) return rc;
+  memset(out, 0, sizeof(*out));
+  if (p->B == 0 || p->n_rows == 0) return RL_OK;
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  Header h;
+  RL_CUDA_CHECK(cudaMemcpyAsync(&h, ws + L.off_hdr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  int32_t* cnt = new int32_t[2 * (size_t)p->B];
+  cudaError_t e1 = cudaMemcpyAsync(cnt, ws + L.off_cnt, (size_t)p->B * 4, cudaMemcpyDeviceToHost, stream);
+  cudaError_t e2 = cudaMemcpyAsync(cnt + p->B, ws + L.off_nsurv, (size_t)p->B * 4, cudaMemcpyDeviceToHost, stream);
+  cudaError_t e3 = cudaStreamSynchronize(stream);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    delete[] cnt;
+    set_error("rl_maxsim_stats: copy failed");
+    return RL_ECUDA;
+  }
+  out->launches = h.launches;
+  out->sample_stride = h.sample_stride;
+  out->cand_cap = h.cand_cap;
+  out->algo = h.algo;
+  out->n_sample_rows = h.n_sample_rows;
+  for (int b = 0; b < p->B; ++b) {
+    out->cand_total += cnt[b];
+    if (cnt[b] > out->cand_max) out->cand_max = cnt[b];
+    out->survivors_total += cnt[p->B + b];
+  }
+  delete[] cnt;
+  return RL_OK;
+}
+
+extern "C" int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t* hit_count, int R, int B,
+                             int H, int num_hits, int k, float* out_sim, int64_t* out_chunk, int32_t* out_count,
+                             void* stream) {
+  RL_REQUIRE(R >= 1 && B >= 0 && H >= 1 && k >= 1 && num_hits >= 0, RL_EINVAL, "rl_topk_merge: bad sizes");
+  if (B == 0) return RL_OK;
+  RL_REQUIRE(hit_sim && hit_chunk && hit_count && out_sim && out_chunk && out_count, RL_EINVAL,
+             "rl_topk_merge: null pointer");
+  MergeArgs m;
+  m.hit_sim = hit_sim; m.hit_chunk = hit_chunk; m.hit_count = hit_count; m.out_sim = out_sim;
+  m.out_chunk = out_chunk; m.out_count = out_count; m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k;
+  return launch_merge(m, (cudaStream_t)stream);
+}

@@ -1,0 +1,453 @@
+// Selection side of the MaxSim scan (sm_100a): query prep, the radix select that turns the sampled
+// scores into per-query emission thresholds, the finalize pass (radix select over the candidate
+// list, exact float64 rescoring with warp-shuffle reductions, bitonic sort, GROUP BY chunk) and the
+// cross-shard merge.
+//
+// Reference semantics restated here: _search.py:75-79 (ORDER BY dist LIMIT num_hits) and
+// _search.py:143-150 (GROUP BY chunk_id, max(sim), ORDER BY sim DESC LIMIT num_results).
+#include "select_finalize.cuh"
+
+namespace rl {
+
+constexpr int kSelThreads = 512;
+constexpr int kBins = 4096;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- block-cooperative order statistic ---------------------------------------------------------
+// Warp 0: find the histogram bin holding the K-th largest element (counting from the top bin).
+// Returns through shared memory: res[0] = bin (or -1 if fewer than K elements), res[1] = count above.
+__device__ void find_bin_from_top(const uint32_t* hist, int K, int* res) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  constexpr int kPer = kBins / 32;
+  uint32_t lane_sum = 0;
+  for (int i = 0; i < kPer; ++i) lane_sum += hist[lane * kPer + i];
+  // inclusive suffix sum over lanes (lane 31 holds the top bins)
+  uint32_t suf = lane_sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  const uint32_t above_lane = suf - lane_sum;  // elements in lanes above this one
+  const bool mine = (above_lane < (uint32_t)K) && (suf >= (uint32_t)K);
+  const uint32_t vote = __ballot_sync(0xffffffffu, mine);
+  if (vote == 0) {
+    if (lane == 0) { res[0] = -1; res[1] = 0; }
+    return;
+  }
+  if (mine) {
+    uint32_t above = above_lane;
+    int bin = lane * kPer + kPer - 1;
+    for (; bin >= lane * kPer; --bin) {
+      const uint32_t h = hist[bin];
+      if (above + h >= (uint32_t)K) break;
+      above += h;
+    }
+    res[0] = bin;
+    res[1] = (int)above;
+  }
+}
+
+// Lower bound (24-bit bin edge, i.e. within 2^-15 relative) of the K-th largest of get(0..n).
+// -inf when fewer than K finite values exist.  All threads of the block must call it.
+template <class Get>
+__device__ float block_kth_largest_lb(int64_t n, int K, Get get, uint32_t* hist, int* res) {
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[f2ord(get(i)) >> 20], 1u);
+  __syncthreads();
+  find_bin_from_top(hist, K, res);
+  __syncthreads();
+  const int bin1 = res[0];
+  const int above1 = res[1];
+  __syncthreads();
+  if (bin1 <= 7) return kNegInf;  // bins 0..7 hold -inf / negative NaN patterns only
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t o = f2ord(get(i));
+    if ((int)(o >> 20) == bin1) atomicAdd(&hist[(o >> 8) & 0xFFFu], 1u);
+  }
+  __syncthreads();
+  find_bin_from_top(hist, K - above1, res);
+  __syncthreads();
+  const int bin2 = res[0] < 0 ? 0 : res[0];
+  __syncthreads();
+  return ord2f(((uint32_t)bin1 << 20) | ((uint32_t)bin2 << 8));
+}
+
+// ---- query prep ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ Q, int B, int d, int metric,
+                                                         int algo, const float* __restrict__ row_stats,
+                                                         double* __restrict__ q_sq, float* __restrict__ q_inv,
+                                                         float* __restrict__ eps) {
+  __shared__ double red[4];
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const double v = Q[(size_t)b * d + c];
+    s += v * v;
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double nq = red[0] + red[1] + red[2] + red[3];
+    q_sq[b] = nq;
+    const float qn = (float)sqrt(nq);
+    q_inv[b] = nq > 0.0 ? (float)(1.0 / sqrt(nq)) : 0.f;
+    const float max_norm = row_stats ? row_stats[0] : 1.f;
+    // Worst-case error of the approximate key in key units.  fp32 scan: accumulation error
+    // <= d * 2^-24 * |q||e| (doubled for slack); fp16-input tcgen05 scan: inputs rounded to 11 bits
+    // => 2^-10 (1 + 2^-11) |q||e| plus fp32 accumulation plus fp16 subnormal absolute terms.
+    const float base = algo == RL_ALGO_TCGEN05 ? (1.25e-3f + (float)(d + 8) * 1.1920929e-7f)
+                                               : (float)(d + 8) * 1.1920929e-7f;
+    float e;
+    if (metric == RL_METRIC_COSINE) e = base;
+    else if (metric == RL_METRIC_DOT) e = base * qn * max_norm;
+    else e = base * (2.f * qn * max_norm + max_norm * max_norm);
+    eps[b] = e;
+  }
+}
+
+// ---- sample select + emit from the dump -----------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
+  __shared__ uint32_t hist[kBins];
+  __shared__ int res[2];
+  const int b = blockIdx.x;
+  const float* dump = a.dump + (size_t)b * a.n_sample_rows;
+  const int64_t n = a.n_sample_rows;
+  float thr;
+  if (a.reuse_thr) {
+    thr = a.thr[b];
+  } else {
+    float T;
+    if (a.mode_sql) {
+      T = block_kth_largest_lb(n, a.sel_k, [&](int64_t i) { return dump[i]; }, hist, res);
+    } else {
+      // chunk-level: a run of sample positions owned by one chunk contributes its max once
+      auto group_max = [&](int64_t p) -> float {
+        const int64_t blk = (p / kBlockRows) * a.S;
+        const int r_in = (int)(p % kBlockRows);
+        const int64_t row = blk * kBlockRows + r_in;
+        if (row >= a.n_rows) return kNegInf;
+        const int32_t c = a.row_chunk[row];
+        if (r_in != 0 && a.row_chunk[row - 1] == c) return kNegInf;  // not the head of its run
+        float m = dump[p];
+        for (int j = 1; r_in + j < kBlockRows && row + j < a.n_rows && a.row_chunk[row + j] == c; ++j)
+          m = fmaxf(m, dump[p + j]);
+        return m;
+      };
+      T = block_kth_largest_lb(n, a.sel_k, group_max, hist, res);
+    }
+    thr = T - 2.f * a.eps[b];
+    if (threadIdx.x == 0) a.thr[b] = thr;
+  }
+  // Sample rows that pass the threshold join the candidate list like any emitted row.
+  for (int64_t p = threadIdx.x; p < n; p += blockDim.x) {
+    const float v = dump[p];
+    if (v >= thr && v > kNegInf) {
+      const int64_t row = (p / kBlockRows) * a.S * kBlockRows + (p % kBlockRows);
+      const int slot = atomicAdd(a.cand_cnt + b, 1);
+      if (slot < a.cap) a.cand[(size_t)b * a.cap + slot] = Cand{v, (int32_t)row};
+    }
+  }
+}
+
+// ---- finalize --------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_sim(int metric, double dot, double ne, double nq) {
+  if (metric == RL_METRIC_COSINE) {
+    double s = dot / sqrt(ne * nq);
+    s = fmin(1.0, fmax(-1.0, s));
+    const float dist = 1.0f - (float)s;  // array_cosine_distance returns FLOAT
+    return 1.0f - dist;                  // sim = 1 - dist (_search.py:72)
+  }
+  if (metric == RL_METRIC_DOT) return 1.0f - (float)(-dot);
+  const double d2 = fmax(0.0, ne + nq - 2.0 * dot);
+  return 1.0f - (float)sqrt(d2);
+}
+
+// Ascending bitonic sort of n (power of two) uint64 keys in shared memory.
+__device__ void bitonic_sort_u64(uint64_t* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t x = keys[i], y = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// flags[i] = 1 when no j < i has the same group id.  O(n^2 / threads); n is a few hundred.
+template <class T>
+__device__ void first_occurrence(const T* ids, int n, uint8_t* flags) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const T c = ids[i];
+    uint8_t f = 1;
+    for (int j = 0; j < i; ++j)
+      if (ids[j] == c) { f = 0; break; }
+    flags[i] = f;
+  }
+  __syncthreads();
+}
+
+// Ordered compaction positions: pos[i] = number of set flags before i.  Single-warp scan (n small).
+__device__ void exclusive_scan_flags(const uint8_t* flags, int n, int* pos) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int f = (i < n) ? flags[i] : 0;
+    // block-wide inclusive scan via warp scans
+    __shared__ int wsum[32];
+    int v = f;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      int s = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += t;
+      }
+      wsum[lane] = s;
+    }
+    __syncthreads();
+    const int before = carry + (w > 0 ? wsum[w - 1] : 0) + v - f;
+    if (i < n) pos[i] = before;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = before + f;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArgs f) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                      // [RL_MAX_SURVIVORS]
+  int32_t* rows = reinterpret_cast<int32_t*>(keys + RL_MAX_SURVIVORS);         // [RL_MAX_SURVIVORS] (later: chunk ids)
+  uint32_t* hist = reinterpret_cast<uint32_t*>(rows + RL_MAX_SURVIVORS);       // kFinalizeScratch bytes
+  float* qv = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(hist) + kFinalizeScratch);  // [d]
+  __shared__ int res[2];
+  __shared__ int s_count;
+
+  const int b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0 && f.header != nullptr) {
+    f.header->launches = f.launches;
+    f.header->sample_stride = f.S;
+    f.header->cand_cap = f.cap;
+    f.header->algo = f.algo;
+    f.header->n_sample_rows = f.n_sample_rows;
+  }
+  const int cnt = f.cand_cnt[b];
+  const int n = min(cnt, f.cap);
+  int st = cnt > f.cap ? RL_STATUS_CAND_OVERFLOW : 0;
+  const Cand* cand = f.cand + (size_t)b * f.cap;
+
+  const float T = block_kth_largest_lb(n, f.sel_k, [&](int64_t i) { return cand[i].key; }, hist, res);
+  const float cut = T - 2.f * f.eps[b];
+  if (threadIdx.x == 0) {
+    f.thr_out[b] = cut;
+    s_count = 0;
+  }
+  for (int c = threadIdx.x; c < f.d; c += blockDim.x) qv[c] = f.Q[(size_t)b * f.d + c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const Cand c = cand[i];
+    if (c.key >= cut) {
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < RL_MAX_SURVIVORS) rows[pos] = c.row;
+    }
+  }
+  __syncthreads();
+  const int ns_all = s_count;
+  const int ns = min(ns_all, RL_MAX_SURVIVORS);
+  if (ns_all > RL_MAX_SURVIVORS) st |= RL_STATUS_TIE_OVERFLOW;
+  int npow2 = 1;
+  while (npow2 < ns) npow2 <<= 1;
+
+  // Exact rescoring: one warp per survivor row, float64 dot / norm, warp-shuffle reduction.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const double nq = f.q_sq[b];
+  const bool vec = (f.d % 4 == 0) && (f.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.E) & 15) == 0);
+  for (int s = warp; s < ns; s += nwarps) {
+    const int32_t row = rows[s];
+    const float* e = f.E + (int64_t)row * f.ld;
+    double dot = 0.0, ne = 0.0;
+    if (vec) {
+      for (int c = lane * 4; c < f.d; c += 128) {
+        const float4 ev = __ldg(reinterpret_cast<const float4*>(e + c));
+        const float4 qq = *reinterpret_cast<const float4*>(qv + c);
+        dot += (double)ev.x * qq.x + (double)ev.y * qq.y + (double)ev.z * qq.z + (double)ev.w * qq.w;
+        ne += (double)ev.x * ev.x + (double)ev.y * ev.y + (double)ev.z * ev.z + (double)ev.w * ev.w;
+      }
+    } else {
+      for (int c = lane; c < f.d; c += 32) {
+        const double ev = __ldg(e + c);
+        dot += ev * qv[c];
+        ne += ev * ev;
+      }
+    }
+    dot = warp_sum_d(dot);
+    ne = warp_sum_d(ne);
+    if (lane == 0) {
+      const float sim = exact_sim(f.metric, dot, ne, nq);
+      keys[s] = ((uint64_t)(~f2ord(sim)) << 32) | (uint32_t)row;  // ascending: sim desc, row asc
+    }
+  }
+  for (int i = ns + threadIdx.x; i < npow2; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(keys, npow2);
+
+  float* out_sim = f.hit_sim + (size_t)b * f.H;
+  int64_t* out_chunk = f.hit_chunk + (size_t)b * f.H;
+  int n_out;
+  if (f.mode_sql) {
+    n_out = min(ns, f.H);
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+      const uint64_t kk = keys[i];
+      out_sim[i] = ord2f(~(uint32_t)(kk >> 32));
+      out_chunk[i] = f.chunk_base + f.row_chunk[(uint32_t)kk];
+    }
+  } else {
+    // exact MaxSim: GROUP BY chunk -> the first occurrence in descending-sim order carries the max.
+    int32_t* chunk = rows;
+    uint8_t* flags = reinterpret_cast<uint8_t*>(hist);
+    int* pos = reinterpret_cast<int*>(hist) + RL_MAX_SURVIVORS / 4;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) chunk[i] = f.row_chunk[(uint32_t)keys[i]];
+    __syncthreads();
+    first_occurrence(chunk, ns, flags);
+    exclusive_scan_flags(flags, ns, pos);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+      if (flags[i] && pos[i] < f.H) {
+        out_sim[pos[i]] = ord2f(~(uint32_t)(keys[i] >> 32));
+        out_chunk[pos[i]] = f.chunk_base + chunk[i];
+      }
+    }
+    __syncthreads();
+    n_out = ns > 0 ? min(f.H, pos[ns - 1] + (int)flags[ns - 1]) : 0;
+  }
+  for (int i = n_out + threadIdx.x; i < f.H; i += blockDim.x) {
+    out_sim[i] = kNegInf;
+    out_chunk[i] = -1;
+  }
+  if (threadIdx.x == 0) {
+    f.hit_count[b] = n_out;
+    f.status[b] = st;
+    f.n_surv[b] = ns_all;
+  }
+}
+
+// ---- cross-shard merge + GROUP BY + LIMIT ------------------------------------------------------------
+constexpr int kMergeMax = 8192;
+
+__global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // [kMergeMax]
+  int64_t* chunk = reinterpret_cast<int64_t*>(keys + kMergeMax);     // [kMergeMax]
+  uint8_t* flags = reinterpret_cast<uint8_t*>(chunk + kMergeMax);    // [kMergeMax]
+  int* pos = reinterpret_cast<int*>(flags + kMergeMax);              // [kMergeMax]
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int r = 0; r < m.R; ++r) {
+    const int cnt = min(m.hit_count[(size_t)r * m.B + b], m.H);
+    __shared__ int base;
+    if (threadIdx.x == 0) { base = s_n; s_n += cnt; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const size_t e = ((size_t)r * m.B + b) * m.H + i;
+      keys[base + i] = ((uint64_t)(~f2ord(m.hit_sim[e])) << 32) | (uint32_t)(r * m.H + i);
+    }
+    __syncthreads();
+  }
+  const int n = s_n;
+  int npow2 = 1;
+  while (npow2 < n) npow2 <<= 1;
+  for (int i = n + threadIdx.x; i < npow2; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(keys, npow2);
+  const int n_keep = m.num_hits > 0 ? min(n, m.num_hits) : n;
+  for (int i = threadIdx.x; i < n_keep; i += blockDim.x) {
+    const uint32_t e = (uint32_t)keys[i];
+    const int r = e / m.H, j = e % m.H;
+    chunk[i] = m.hit_chunk[((size_t)r * m.B + b) * m.H + j];
+  }
+  __syncthreads();
+  first_occurrence(chunk, n_keep, flags);
+  exclusive_scan_flags(flags, n_keep, pos);
+  float* out_sim = m.out_sim + (size_t)b * m.k;
+  int64_t* out_chunk = m.out_chunk + (size_t)b * m.k;
+  for (int i = threadIdx.x; i < n_keep; i += blockDim.x) {
+    if (flags[i] && pos[i] < m.k) {
+      out_sim[pos[i]] = ord2f(~(uint32_t)(keys[i] >> 32));
+      out_chunk[pos[i]] = chunk[i];
+    }
+  }
+  __syncthreads();
+  const int n_out = n_keep > 0 ? min(m.k, pos[n_keep - 1] + (int)flags[n_keep - 1]) : 0;
+  for (int i = n_out + threadIdx.x; i < m.k; i += blockDim.x) {
+    out_sim[i] = kNegInf;
+    out_chunk[i] = -1;
+  }
+  if (threadIdx.x == 0) m.out_count[b] = n_out;
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+int launch_query_prep(const float* Q, int B, int d, int metric, int algo, const float* row_stats, double* q_sq,
+                      float* q_inv, float* eps, cudaStream_t stream) {
+  query_prep_kernel<<<B, 128, 0, stream>>>(Q, B, d, metric, algo, row_stats, q_sq, q_inv, eps);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+int launch_select(const SelectArgs& a, int B, cudaStream_t stream) {
+  select_kernel<<<B, kSelThreads, 0, stream>>>(a);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+size_t finalize_smem_bytes(int d) {
+  return (size_t)RL_MAX_SURVIVORS * (8 + 4) + (size_t)kFinalizeScratch + (size_t)d * 4;
+}
+
+int launch_finalize(const FinalizeArgs& f, int B, cudaStream_t stream) {
+  static_assert(kFinalizeScratch >= kBins * 4 && kFinalizeScratch >= RL_MAX_SURVIVORS * 5, "scratch reuse");
+  const size_t smem = finalize_smem_bytes(f.d);
+  RL_REQUIRE(smem <= 220 * 1024, RL_EUNSUPPORTED, "finalize: d=%d too large", f.d);
+  RL_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  finalize_kernel<<<B, kSelThreads, smem, stream>>>(f);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+int launch_merge(const MergeArgs& m, cudaStream_t stream) {
+  RL_REQUIRE((int64_t)m.R * m.H <= kMergeMax, RL_EUNSUPPORTED, "rl_topk_merge: R*H=%lld exceeds %d",
+             (long long)m.R * m.H, kMergeMax);
+  const size_t smem = (size_t)kMergeMax * (8 + 8 + 1 + 4);
+  RL_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_kernel<<<m.B, kSelThreads, smem, stream>>>(m);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+}  // namespace rl

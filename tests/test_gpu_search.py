@@ -1,0 +1,271 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle on seeded inputs."""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+from fake_llama import FakeLlama
+from parity import check_exact_maxsim, check_sql_semantics
+from synth import make_corpus, make_queries, random_orthogonal
+
+from oracle import pool as opool
+from oracle import vector_search as ovs
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["fp32", "tcgen05"]
+
+
+@pytest.fixture(scope="module")
+def rl():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import raglite_b200
+
+    return raglite_b200
+
+
+def _algo_ok(rl, algo, d, metric="cosine"):
+    if algo == "tcgen05":
+        from raglite_b200 import _lib
+        import ctypes
+
+        p = _lib.ScanParams()
+        p.n_rows, p.d, p.ld, p.B, p.k, p.metric, p.max_vecs_per_chunk = 1024, d, d, 1, 1, _lib.RL_METRIC[metric], 1
+        p.E = 256
+        p.algo = 2
+        if _lib.load().rl_maxsim_workspace_bytes(ctypes.byref(p)) == 0:
+            pytest.skip("tcgen05 scan does not support this shape/metric")
+
+
+def test_row_stats_and_chunk_map(rl):
+    E, off = make_corpus(300, (1, 9), 100, seed=1, normalize=False)
+    idx = rl.CorpusIndex(E, off)
+    nrm = np.linalg.norm(E.astype(np.float64), axis=1)
+    assert np.allclose(idx.inv_norm.cpu().numpy(), 1 / nrm, rtol=1e-6)
+    assert np.allclose(idx.sq_norm.cpu().numpy(), nrm**2, rtol=1e-6)
+    assert np.array_equal(idx.row_chunk.cpu().numpy(), ovs.row_to_chunk(off).astype(np.int32))
+    st = idx.stats.cpu().numpy()
+    assert np.isclose(st[0], nrm.max(), rtol=1e-6) and np.isclose(st[1], np.abs(E).max(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_adapter_apply_matches_reference_expression(rl, dtype):
+    import torch
+
+    d = 96
+    A = random_orthogonal(d, seed=5)
+    Q = make_queries(np.zeros((0, d), np.float32), 37, seed=3).astype(dtype)
+    idx = rl.CorpusIndex(np.eye(d, dtype=np.float32))
+    idx.set_query_adapter(A)
+    got = idx.apply_adapter(torch.from_numpy(Q.astype(np.float32)).cuda(), round_fp16=(dtype == np.float16)).cpu().numpy()
+    want = np.stack([ovs.apply_query_adapter(A, q) for q in Q])      # (A @ q).astype(q.dtype), _search.py:62
+    assert want.dtype == dtype
+    mism = got != want.astype(np.float32)
+    assert mism.mean() < 1e-3                                          # rounding-boundary cases only
+    assert np.allclose(got, want.astype(np.float32), atol=2e-3 if dtype == np.float16 else 1e-6)
+
+
+@pytest.mark.parametrize("name", ["pool_small", "pool_multi", "pool_nonorm", "pool_wide"])
+def test_late_chunking_pool_matches_reference_golden(rl, golden_dir, name):
+    from raglite_b200 import _embed
+
+    z = np.load(golden_dir / f"{name}.npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    llm = FakeLlama(n_ctx=meta["n_ctx"], dim=meta["dim"], seed=meta["seed"])
+    cfg = rl.RAGLiteConfig(embedder="llama-cpp-python/fake/fake.gguf@64", embedder_normalize=meta["normalize"], reranker=None)
+    rl.register_token_embedder(cfg.embedder, llm)
+    got = rl.embed_strings(meta["sentences"], config=cfg)
+    want = z["late_chunking"]
+    assert got.dtype == np.float16 and got.shape == want.shape            # tests/test_embed.py:24
+    assert np.all(np.isfinite(got))
+    ulp = np.abs(got.view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 1e-3
+    simple = _embed.embed_strings_without_late_chunking(meta["sentences"][:7], config=cfg)
+    ulp = np.abs(simple.view(np.int16).astype(np.int32) - z["simple"].view(np.int16).astype(np.int32))
+    assert ulp.max() <= 1 and (ulp > 0).mean() < 1e-3
+    assert np.array_equal(opool.embed_with_llama(meta["sentences"], llm, normalize=meta["normalize"]).view(np.uint16),
+                          want.view(np.uint16))
+
+
+CASES = [
+    # n_chunks, vecs, dim, B, k, seed
+    (1000, 1, 384, 4, 5, 0),        # BASELINE configs[0]: 1k chunks x 1 vec x 384 (bge-small)
+    (700, 8, 64, 9, 20, 1),
+    (513, (1, 16), 128, 5, 10, 2),  # variable vectors per chunk (CSR coverage)
+    (3000, 4, 32, 3, 3, 3),
+    (40, 3, 16, 2, 8, 4),           # fewer chunks than some k * oversample
+]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("case", CASES)
+def test_vector_search_batch_sql_semantics(rl, case, algo):
+    n_chunks, vecs, dim, B, k, seed = case
+    _algo_ok(rl, algo, dim)
+    E, off = make_corpus(n_chunks, vecs, dim, seed=seed)
+    Q = make_queries(E, B, seed=seed + 100)
+    idx = rl.CorpusIndex(E, off)
+    cfg = rl.RAGLiteConfig(reranker=None)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=k, config=cfg, index=idx, algo=algo)
+    for b in range(B):
+        n = counts[b]
+        check_sql_semantics(E, off, Q[b], ids[b, :n], sims[b, :n], k=k)
+        assert np.all(ids[b, n:] == -1)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("case", CASES)
+def test_vector_search_batch_exact_maxsim(rl, case, algo):
+    n_chunks, vecs, dim, B, k, seed = case
+    _algo_ok(rl, algo, dim)
+    E, off = make_corpus(n_chunks, vecs, dim, seed=seed)
+    Q = make_queries(E, B, seed=seed + 200)
+    idx = rl.CorpusIndex(E, off)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=k, config=rl.RAGLiteConfig(reranker=None), index=idx,
+                                               exact_maxsim=True, algo=algo)
+    for b in range(B):
+        n = counts[b]
+        assert n == min(k, n_chunks)
+        check_exact_maxsim(E, off, Q[b], ids[b, :n], sims[b, :n], k=k)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("metric", ["cosine", "dot", "l2"])
+def test_metrics(rl, metric, algo):
+    _algo_ok(rl, algo, 48, metric)
+    E, off = make_corpus(900, (1, 6), 48, seed=7, normalize=False)
+    E *= np.random.default_rng(1).uniform(0.5, 2.0, size=(E.shape[0], 1)).astype(np.float32)
+    Q = 1.7 * make_queries(E, 6, seed=8)
+    idx = rl.CorpusIndex(E, off)
+    cfg = rl.RAGLiteConfig(vector_search_distance_metric=metric, reranker=None)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=7, config=cfg, index=idx, algo=algo)
+    ids2, sims2, counts2 = rl.vector_search_batch(Q, num_results=7, config=cfg, index=idx, algo=algo, exact_maxsim=True)
+    for b in range(len(Q)):
+        check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=7, metric=metric)
+        check_exact_maxsim(E, off, Q[b], ids2[b, :counts2[b]], sims2[b, :counts2[b]], k=7, metric=metric)
+
+
+@pytest.mark.parametrize("d", [3, 17, 50])
+def test_odd_dimensions_take_the_fp32_scan(rl, d):
+    E, off = make_corpus(400, 2, d, seed=d)
+    Q = make_queries(E, 3, seed=d + 1)
+    idx = rl.CorpusIndex(E, off)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=5, config=rl.RAGLiteConfig(reranker=None), index=idx)
+    for b in range(3):
+        check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=5)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_sampled_two_pass_path_and_oversample_rule(rl, algo):
+    """Corpus large enough that the scan samples (S > 1) and the emit pass runs; chunk_max_size and
+    oversample change num_hits as in _search.py:66-67."""
+    _algo_ok(rl, algo, 64)
+    E, off = make_corpus(6000, 8, 64, seed=11)
+    Q = make_queries(E, 16, seed=12)
+    idx = rl.CorpusIndex(E, off)
+    cfg = rl.RAGLiteConfig(chunk_max_size=1024, reranker=None)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=20, oversample=6, config=cfg, index=idx, algo=algo)
+    st = idx.scan_stats()
+    assert st["sample_stride"] > 1 and st["launches"] >= 5
+    for b in range(len(Q)):
+        check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=20, oversample=6, chunk_max_size=1024)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=20, config=cfg, index=idx, algo=algo, exact_maxsim=True)
+    for b in range(len(Q)):
+        check_exact_maxsim(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=20)
+
+
+def test_candidate_overflow_retry(rl):
+    """Adversarial order: rows sorted by similarity to the query, tiny candidate capacity."""
+    import torch
+
+    E, off = make_corpus(4000, 4, 32, seed=21)
+    q = make_queries(E, 1, seed=22)
+    order = np.argsort(E @ q[0])          # ascending similarity: every later block beats the sample
+    E = np.ascontiguousarray(E[order])
+    idx = rl.CorpusIndex(E, off)
+    Q = torch.from_numpy(q).cuda()
+    res = idx.scan(Q, k=10, num_hits=40, sample_stride=16, cand_cap=256, algo="fp32")
+    assert int(res.status.cpu()[0]) & 1   # overflow reported
+    res = idx.scan_checked(Q, k=10, num_hits=40, sample_stride=16, cand_cap=256, algo="fp32")
+    assert int(res.status.cpu()[0]) == 0
+    sim, chunk, count = rl.merge_hits(res.hit_sim, res.hit_chunk, res.hit_count, num_hits=40, k=10)
+    n = int(count[0])
+    check_sql_semantics(E, off, q[0], chunk[0, :n].cpu().numpy(), sim[0, :n].cpu().numpy(), k=10)
+
+
+def test_duplicates_and_ties(rl):
+    E, off = make_corpus(300, 4, 32, seed=31)
+    E[400:440] = E[7]                      # 40 identical vectors spread over 10 chunks
+    Q = E[[7]].copy()
+    idx = rl.CorpusIndex(E, off)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=5, config=rl.RAGLiteConfig(reranker=None), index=idx,
+                                               exact_maxsim=True)
+    assert counts[0] == 5 and np.allclose(sims[0], 1.0, atol=1e-6)
+    s = ovs.maxsim_scores(E, off, Q[0])
+    assert np.allclose(s[ids[0]], 1.0, atol=1e-9)
+
+
+def test_empty_database_and_tiny_inputs(rl):
+    cfg = rl.RAGLiteConfig(db_url="mem://empty", reranker=None)
+    idx = rl.CorpusIndex(np.zeros((0, 16), np.float32))
+    rl.register_index(cfg, idx)
+    ids, scores = rl.vector_search(np.ones(16, np.float32), num_results=5, config=cfg)
+    assert ids == [] and scores == []     # tests/test_search.py:76-85
+    E, off = make_corpus(1, 1, 16, seed=1)
+    idx = rl.CorpusIndex(E, off, chunk_ids=["only"])
+    rl.register_index(cfg, idx)
+    ids, scores = rl.vector_search(E[0].astype(np.float16), num_results=5, config=cfg)
+    assert ids == ["only"] and isinstance(scores[0], float) and abs(scores[0] - 1.0) < 1e-3
+
+
+def test_vector_search_dropin_with_adapter_and_metadata(rl):
+    E, off = make_corpus(500, (1, 5), 64, seed=41, fp16_round=True)
+    n_chunks = len(off) - 1
+    meta = [{"topic": ["Physics"] if c % 3 == 0 else ["Math"], "type": ["Paper"]} for c in range(n_chunks)]
+    cfg = rl.RAGLiteConfig(db_url="mem://dropin", reranker=None)
+    idx = rl.CorpusIndex(E, off, chunk_ids=[f"chunk-{c}" for c in range(n_chunks)], chunk_metadata=meta)
+    A = random_orthogonal(64, seed=9)
+    idx.set_query_adapter(A)
+    rl.register_index(cfg, idx)
+    q = make_queries(E, 1, seed=42)[0].astype(np.float16)      # string queries arrive as fp16 (_embed.py:140)
+    ids, scores = rl.vector_search(q, num_results=5, config=cfg)
+    assert len(ids) == len(scores) == 5 and all(isinstance(i, str) for i in ids) and all(isinstance(s, float) for s in scores)
+    got = [int(i.split("-")[1]) for i in ids]
+    check_sql_semantics(E, off, q, got, scores, k=5, adapter=A)
+    cfg_off = rl.RAGLiteConfig(db_url="mem://dropin", vector_search_query_adapter=False, reranker=None)
+    _, scores_no = rl.vector_search(q, num_results=5, config=cfg_off)
+    assert scores != scores_no                                  # tests/test_query_adapter.py:37-40
+    allowed = np.array([c % 3 == 0 for c in range(n_chunks)])
+    ids_f, sc_f = rl.vector_search(q, num_results=5, metadata_filter={"type": "Paper", "topic": "Physics"}, config=cfg)
+    got = [int(i.split("-")[1]) for i in ids_f]
+    assert 0 < len(got) <= 5 and all(g % 3 == 0 for g in got)    # tests/test_search.py:88-127
+    check_sql_semantics(E, off, q, got, sc_f, k=5, adapter=A, allowed_chunks=allowed)
+    ids_e, _ = rl.vector_search(q, num_results=5, metadata_filter={"type": "Paper", "topic": "Chemistry"}, config=cfg)
+    assert ids_e == []
+
+
+def test_two_shards_merge_equals_single_index(rl):
+    import torch
+
+    E, off = make_corpus(2000, (1, 8), 64, seed=51)
+    Q = make_queries(E, 8, seed=52)
+    cut_chunk = 900
+    cut_row = int(off[cut_chunk])
+    a = rl.CorpusIndex(E[:cut_row], off[: cut_chunk + 1])
+    b = rl.CorpusIndex(E[cut_row:], off[cut_chunk:] - cut_row, chunk_base=cut_chunk)
+    Qd = torch.from_numpy(Q).cuda()
+    for num_hits in (80, 0):
+        ra = a.scan_checked(Qd, k=20, num_hits=num_hits)
+        rb = b.scan_checked(Qd, k=20, num_hits=num_hits)
+        sim, chunk, count = rl.merge_hits(torch.stack([ra.hit_sim, rb.hit_sim]), torch.stack([ra.hit_chunk, rb.hit_chunk]),
+                                          torch.stack([ra.hit_count, rb.hit_count]), num_hits=num_hits, k=20)
+        sim, chunk, count = sim.cpu().numpy(), chunk.cpu().numpy(), count.cpu().numpy()
+        for i in range(len(Q)):
+            if num_hits:
+                check_sql_semantics(E, off, Q[i], chunk[i, :count[i]], sim[i, :count[i]], k=20)
+            else:
+                check_exact_maxsim(E, off, Q[i], chunk[i, :count[i]], sim[i, :count[i]], k=20)
