@@ -139,6 +139,12 @@ int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stat
  * last one.  Diagnostics for bench.py's roofline figure. */
 int rl_maxsim_kernel_times(const void* workspace, float* ms);
 
+/* Debug/test hook: copy the sampled approximate keys of the last call (float32 [B, n_sample_rows],
+ * sample position p <-> row (p / 128) * sample_stride * 128 + p % 128) into dst (device memory);
+ * *n_sample_rows receives the row count.  dst may be NULL to query the size only. */
+int rl_maxsim_copy_dump(const rl_scan_params* p, const void* workspace, float* dst, int64_t* n_sample_rows,
+                        void* stream);
+
 /* ---- Shard merge + GROUP BY chunk + top-k: _search.py:143-150 --------------------------------
  * hit_*[R,B,H] are the per-shard outputs of rl_maxsim_topk (all-gathered).  num_hits > 0: keep
  * the num_hits best vectors overall, group by chunk (max sim), order desc, limit k.  num_hits == 0:

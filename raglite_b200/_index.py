@@ -213,6 +213,17 @@ class CorpusIndex:
                   "rl_maxsim_stats")
         return {name: int(getattr(st, name)) for name, _ in ScanStats._fields_}
 
+    def debug_dump(self) -> torch.Tensor:
+        """Sampled approximate keys ``[B, n_sample_rows]`` of the last scan (test hook)."""
+        n = C.c_int64(0)
+        p = self.last_params
+        check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self._ws), None, C.byref(n), _stream()), "rl_maxsim_copy_dump")
+        out = torch.empty((int(p.B), int(n.value)), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self._ws), _ptr(out), C.byref(n), _stream()),
+                  "rl_maxsim_copy_dump")
+        return out
+
     def kernel_times_ms(self) -> dict[str, float]:
         """Stage times of the last scan made with ``flags=RL_FLAG_TIME_KERNELS`` (synchronises)."""
         ms = (C.c_float * 5)()

@@ -302,6 +302,20 @@ extern "C" int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, r
   return RL_OK;
 }
 
+extern "C" int rl_maxsim_copy_dump(const rl_scan_params* p, const void* workspace, float* dst, int64_t* n_sample_rows,
+                                   void* stream) {
+  RL_REQUIRE(p && workspace && n_sample_rows, RL_EINVAL, "rl_maxsim_copy_dump: null pointer");
+  Layout L;
+  int rc = make_layout(p, 148, &L);
+  if (rc != RL_OK) return rc;
+  *n_sample_rows = L.n_sample_rows;
+  if (dst != nullptr && p->B > 0 && L.n_sample_rows > 0) {
+    RL_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const unsigned char*>(workspace) + L.off_dump,
+                                  (size_t)p->B * L.n_sample_rows * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return RL_OK;
+}
+
 extern "C" int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t* hit_count, int R, int B,
                              int H, int num_hits, int k, float* out_sim, int64_t* out_chunk, int32_t* out_count,
                              void* stream) {

@@ -1,15 +1,485 @@
-// tcgen05 / TMEM scan -- placeholder until the kernel lands (next commit).
+// tcgen05 / TMEM scan (RL_ALGO_TCGEN05) for sm_100a.
+//
+// Replaces the per-row distance expression DuckDB evaluates for vector_search (reference
+// _search.py:69-79, _typing.py:123-134) with a coarse tensor-core pass whose survivors are
+// re-scored exactly in float64 by the finalize kernel (select_finalize.cu).
+//
+// One persistent CTA per SM walks its tiles of 128 corpus rows:
+//   * 8 loader warps stream the fp32 rows from HBM with coalesced 128-bit loads, scale them (cosine:
+//     1/|e|, dot/l2: a global power of two), round to fp16 and store them into a 128B-swizzled
+//     K-major shared-memory tile (the UMMA A operand),
+//   * one thread bulk-copies (cp.async.bulk, the TMA engine) the matching 64-wide K slice of the
+//     pre-swizzled fp16 query image (the UMMA B operand, N = #queries <= 256),
+//   * one thread issues tcgen05.mma (M=128, N=#queries, K=16, fp32 accumulate in TMEM); two
+//     accumulator buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1,
+//   * 4 epilogue warps read the accumulators with tcgen05.ld (lane = corpus row, column = query),
+//     turn them into keys and either dump them (sample tiles) or compare them with the per-query
+//     threshold and append the few survivors to the candidate lists.
+// All hand-offs are mbarrier based (full/empty per smem stage, full/empty per TMEM buffer).
+#include <cuda_fp16.h>
+
 #include "scan_tcgen05.cuh"
 
 namespace rl {
-bool tcgen05_supported(const rl_scan_params*) { return false; }
-size_t tcgen05_qimg_bytes(int, int) { return 0; }
-int tcgen05_prepare_queries(const rl_scan_params*, const float*, float*, void*, cudaStream_t) {
-  set_error("tcgen05 scan not built");
-  return RL_EUNSUPPORTED;
+
+namespace {
+
+constexpr int kTileM = 128;           // corpus rows per tile (UMMA M)
+constexpr int kSliceK = 64;           // fp16 elements per K slice = one 128-byte swizzle row
+constexpr int kMaxQ = 256;            // queries per pass (UMMA N <= 256)
+constexpr int kNumEpiWarps = 4;       // warps 0..3 (TMEM lane quarter == warp index)
+constexpr int kMmaWarp = 4;
+constexpr int kQWarp = 5;
+constexpr int kFirstLoaderWarp = 6;
+constexpr int kNumLoaderWarps = 8;
+constexpr int kThreads = (kFirstLoaderWarp + kNumLoaderWarps) * 32;  // 448
+constexpr int kMaxStages = 8;
+constexpr int kABytes = kTileM * 128;  // 16 KB per stage
+constexpr uint32_t kSmemBudget = 222 * 1024;
+
+struct TcArgs {
+  ScanArgs a;
+  const __half* qimg;     // [n_ks][nq][64] fp16, rows pre-swizzled
+  const float* q_scale;   // [B] key = acc * q_scale[b] (+ bias)
+  const float* row_stats; // [2] max norm, max |element|
+  int nq;                 // padded #queries of this pass (multiple of 16)
+  int n_ks;               // K slices
+  int stages;
+  int tmem_cols;          // allocated TMEM columns (power of two >= 2 * buf_cols)
+  int buf_cols;           // columns per accumulator buffer (nq rounded up to 32)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-int launch_scan_tcgen05(const ScanArgs&, const rl_scan_params*, const float*, const void*, int, cudaStream_t) {
-  set_error("tcgen05 scan not built");
-  return RL_EUNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=F16 (0), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Global power-of-two row scale for the dot / l2 metrics (keeps |x| <= 1 in fp16).
+__device__ __forceinline__ float pow2_scale(float max_abs) {
+  return max_abs > 0.f ? exp2f(-ceilf(log2f(max_abs))) : 1.f;
+}
+
+struct SmemLayout {
+  unsigned char* stage_base;  // stages * (kABytes + nq*128)
+  uint64_t* full;             // [kMaxStages]
+  uint64_t* empty;            // [kMaxStages]
+  uint64_t* tmem_full;        // [2]
+  uint64_t* tmem_empty;       // [2]
+  uint32_t* tmem_ptr;
+  float* thr;                 // [kMaxQ]
+  float* cs;                  // [kMaxQ]
+};
+
+__host__ __device__ inline uint32_t stage_bytes(int nq) { return kABytes + (uint32_t)nq * 128u; }
+__host__ __device__ inline uint32_t tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 * kMaxQ * 4; }
+
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs t) {
+  extern __shared__ unsigned char smem_dyn[];
+  const ScanArgs& a = t.a;
+  // 1024-byte alignment for the 128B-swizzled tiles.
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbytes = stage_bytes(t.nq);
+  SmemLayout s;
+  s.stage_base = base;
+  s.full = reinterpret_cast<uint64_t*>(base + (size_t)t.stages * sbytes);
+  s.empty = s.full + kMaxStages;
+  s.tmem_full = s.empty + kMaxStages;
+  s.tmem_empty = s.tmem_full + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
+  s.thr = reinterpret_cast<float*>(s.tmem_ptr + 4);
+  s.cs = s.thr + kMaxQ;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = a.n_mode_blocks;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < t.stages; ++i) {
+      mbar_init(&s.full[i], kNumLoaderWarps + 1);  // 8 loader warps + the query producer (expect_tx)
+      mbar_init(&s.empty[i], 1);                   // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      mbar_init(&s.tmem_empty[i], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < kMaxQ; i += blockDim.x) {
+    s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
+    s.cs[i] = (i < a.B) ? t.q_scale[i] : 0.f;
+  }
+  if (warp == kMmaWarp) tmem_alloc(s.tmem_ptr, (uint32_t)t.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+
+  if (warp >= kFirstLoaderWarp) {
+    // ===== corpus loaders: HBM fp32 -> registers -> fp16 -> swizzled smem (UMMA A operand) =====
+    const int lt = threadIdx.x - kFirstLoaderWarp * 32;  // 0..255
+    const int c4 = lt & 15;                              // float4 column within the 64-wide K slice
+    const int r0 = lt >> 4;                              // rows r0 + 16 i, i = 0..7
+    const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
+    const int64_t total_items = my_tiles * t.n_ks;
+    float4 cur[8], nxt[8];
+    float rs[8];
+
+    auto issue = [&](int64_t item, float4 (&buf)[8]) {
+      const int64_t tile = item / t.n_ks;
+      const int ks = (int)(item - tile * t.n_ks);
+      const int64_t blk = mode_block_index(a, first + tile * stride);
+      const int col = ks * kSliceK + c4 * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = blk * kTileM + r0 + 16 * i;
+        if (row < a.n_rows && col < a.d) buf[i] = ldg_stream(a.E + row * a.ld + col);
+        else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto load_scales = [&](int64_t tile) {
+      const int64_t blk = mode_block_index(a, first + tile * stride);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = blk * kTileM + r0 + 16 * i;
+        rs[i] = (METRIC == RL_METRIC_COSINE) ? (row < a.n_rows ? __ldg(a.inv_norm + row) : 0.f) : gscale;
+      }
+    };
+
+    if (total_items > 0) issue(0, cur);
+    for (int64_t item = 0; item < total_items; ++item) {
+      const int ks = (int)(item % t.n_ks);
+      if (ks == 0) load_scales(item / t.n_ks);
+      if (item + 1 < total_items) issue(item + 1, nxt);
+      const int stage = (int)(item % t.stages);
+      const uint32_t phase = (uint32_t)((item / t.stages) & 1);
+      mbar_wait(&s.empty[stage], phase ^ 1u);
+      unsigned char* A = s.stage_base + (size_t)stage * sbytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        const __half2 h01 = __floats2half2_rn(cur[i].x * rs[i], cur[i].y * rs[i]);
+        const __half2 h23 = __floats2half2_rn(cur[i].z * rs[i], cur[i].w * rs[i]);
+        uint2 packed;
+        packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+        packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+        // 16-byte chunk j = c4/2 lands at chunk (j ^ (r & 7)); this thread owns half of it.
+        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+        *reinterpret_cast<uint2*>(A + off) = packed;
+      }
+      fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[stage]);
+      if (item + 1 < total_items) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      }
+    }
+  } else if (warp == kQWarp) {
+    // ===== query producer: bulk-copy the pre-swizzled fp16 K slice of all queries (UMMA B operand) =====
+    if (lane == 0) {
+      const uint32_t qbytes = (uint32_t)t.nq * 128u;
+      const int64_t total_items = my_tiles * t.n_ks;
+      for (int64_t item = 0; item < total_items; ++item) {
+        const int ks = (int)(item % t.n_ks);
+        const int stage = (int)(item % t.stages);
+        const uint32_t phase = (uint32_t)((item / t.stages) & 1);
+        mbar_wait(&s.empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&s.full[stage], qbytes);
+        bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes,
+                 reinterpret_cast<const unsigned char*>(t.qimg) + (size_t)ks * qbytes, qbytes, &s.full[stage]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===== MMA issuer: one thread drives the tensor core =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, t.nq);
+      int64_t item = 0;
+      for (int64_t tile = 0; tile < my_tiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        mbar_wait(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * t.buf_cols);
+        for (int ks = 0; ks < t.n_ks; ++ks, ++item) {
+          const int stage = (int)(item % t.stages);
+          const uint32_t phase = (uint32_t)((item / t.stages) & 1);
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.stage_base + (size_t)stage * sbytes);
+          const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
+          const uint64_t b_desc = make_kmajor_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kSliceK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the swizzled row: +2 in the >>4 encoding
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&s.empty[stage]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&s.tmem_full[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3: TMEM -> registers -> key -> dump / threshold + emit =====
+    const int q = warp;  // TMEM lane quarter
+    for (int64_t tile = 0; tile < my_tiles; ++tile) {
+      const int buf = (int)(tile & 1);
+      const int64_t ord = first + tile * stride;
+      const int64_t blk = mode_block_index(a, ord);
+      const int r_in = q * 32 + lane;
+      const int64_t row = blk * kTileM + r_in;
+      bool valid = row < a.n_rows;
+      if (valid && a.row_allowed != nullptr) valid = a.row_allowed[row] != 0;
+      const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
+      mbar_wait(&s.tmem_full[buf], (uint32_t)((tile >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * t.buf_cols);
+      for (int c0 = 0; c0 < t.nq; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr0 + (uint32_t)c0, v);
+        if (a.dump_mode) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c0 + j;
+            if (col < a.B) {
+              float key = __uint_as_float(v[j]);
+              if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
+              a.dump[(size_t)col * a.n_sample_rows + ord * kTileM + r_in] = valid ? key : kNegInf;
+            }
+          }
+        } else {
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float key = __uint_as_float(v[j]);
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
+            any |= key >= s.thr[c0 + j];
+          }
+          if (any && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float key = __uint_as_float(v[j]);
+              if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
+              if (key >= s.thr[c0 + j]) emit_candidate(a, c0 + j, key, (int32_t)row);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)t.tmem_cols);
+  }
+}
+
+// Query image: fp16, scaled, laid out exactly as the swizzled smem stage rows.
+__global__ void __launch_bounds__(128) query_image_kernel(const float* __restrict__ Q, int B, int d, int metric,
+                                                          const float* __restrict__ q_inv_norm,
+                                                          const float* __restrict__ row_stats, float* __restrict__ q_scale,
+                                                          __half* __restrict__ qimg, int n_ks) {
+  __shared__ float red[4];
+  const int b = blockIdx.x;
+  const int group = b / kMaxQ, n = b % kMaxQ;
+  const int nq = min(kMaxQ, (B - group * kMaxQ + 15) / 16 * 16);
+  const float* q = Q + (size_t)b * d;
+  float scale;
+  if (metric == RL_METRIC_COSINE) {
+    scale = q_inv_norm[b];
+    if (threadIdx.x == 0) q_scale[b] = 1.f;
+  } else {
+    float m = 0.f;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) m = fmaxf(m, fabsf(q[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    scale = pow2_scale(m);
+    const float rs_e = pow2_scale(row_stats[1]);
+    if (threadIdx.x == 0) q_scale[b] = (metric == RL_METRIC_L2 ? 2.f : 1.f) / (scale * rs_e);
+  }
+  __half* img = qimg + (size_t)group * n_ks * kMaxQ * kSliceK;  // groups are laid out with the full 256-row pitch
+  for (int c = threadIdx.x; c < n_ks * kSliceK; c += blockDim.x) {
+    const int ks = c / kSliceK, e = c % kSliceK;
+    const float v = c < d ? q[c] * scale : 0.f;
+    const int chunk = e >> 3, within = e & 7;
+    const size_t off = ((size_t)ks * nq + n) * kSliceK + (size_t)(((chunk ^ (n & 7)) << 3) + within);
+    img[off] = __float2half_rn(v);
+  }
+}
+
+}  // namespace
+
+bool tcgen05_supported(const rl_scan_params* p) {
+  if (p == nullptr || p->n_rows <= 0 || p->B <= 0) return false;
+  if (p->d % 4 != 0 || p->ld % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p->E) & 15) != 0) return false;
+  if ((p->d + kSliceK - 1) / kSliceK > 1024) return false;
+  return true;
+}
+
+size_t tcgen05_qimg_bytes(int B, int d) {
+  const int n_ks = (d + kSliceK - 1) / kSliceK;
+  const int groups = (B + kMaxQ - 1) / kMaxQ;
+  return (size_t)groups * n_ks * kMaxQ * kSliceK * sizeof(__half);
+}
+
+int tcgen05_prepare_queries(const rl_scan_params* p, const float* q_inv_norm, float* q_scale, void* qimg,
+                            cudaStream_t stream) {
+  const int n_ks = (p->d + kSliceK - 1) / kSliceK;
+  RL_CUDA_CHECK(cudaMemsetAsync(qimg, 0, tcgen05_qimg_bytes(p->B, p->d), stream));
+  query_image_kernel<<<p->B, 128, 0, stream>>>(p->Q, p->B, p->d, p->metric, q_inv_norm, p->row_stats, q_scale,
+                                                 reinterpret_cast<__half*>(qimg), n_ks);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const float* q_scale, const void* qimg,
+                        int sm_count, cudaStream_t stream) {
+  if (a_in.n_mode_blocks == 0 || a_in.B == 0) return RL_OK;
+  const int n_ks = (p->d + kSliceK - 1) / kSliceK;
+  const int groups = (a_in.B + kMaxQ - 1) / kMaxQ;
+  for (int g = 0; g < groups; ++g) {
+    TcArgs t;
+    t.a = a_in;
+    const int q0 = g * kMaxQ;
+    const int nb = a_in.B - q0 < kMaxQ ? a_in.B - q0 : kMaxQ;
+    t.a.B = nb;
+    t.a.thr = a_in.thr + q0;
+    t.a.dump = a_in.dump + (size_t)q0 * a_in.n_sample_rows;
+    t.a.cand = a_in.cand + (size_t)q0 * a_in.cap;
+    t.a.cand_cnt = a_in.cand_cnt + q0;
+    t.a.q_inv_norm = a_in.q_inv_norm + q0;
+    t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g * n_ks * kMaxQ * kSliceK;
+    t.q_scale = q_scale + q0;
+    t.row_stats = p->row_stats;
+    t.nq = (nb + 15) / 16 * 16;
+    t.n_ks = n_ks;
+    t.buf_cols = (t.nq + 31) / 32 * 32;
+    int cols = 32;
+    while (cols < 2 * t.buf_cols) cols *= 2;
+    t.tmem_cols = cols;
+    const uint32_t avail = kSmemBudget - 1024 - tail_bytes();
+    int stages = (int)(avail / stage_bytes(t.nq));
+    if (stages > kMaxStages) stages = kMaxStages;
+    RL_REQUIRE(stages >= 2, RL_EUNSUPPORTED, "tcgen05 scan: not enough shared memory for 2 stages");
+    t.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes(t.nq) + tail_bytes() + 1024;
+    RL_REQUIRE(p->row_stats != nullptr, RL_EINVAL, "tcgen05 scan needs row_stats");
+    const int grid = (int)(a_in.n_mode_blocks < sm_count ? a_in.n_mode_blocks : sm_count);
+    auto launch = [&](auto kernel) -> int {
+      RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<grid, kThreads, smem, stream>>>(t);
+      RL_CUDA_CHECK(cudaGetLastError());
+      return RL_OK;
+    };
+    int rc;
+    if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE>);
+    else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT>);
+    else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2>);
+    if (rc != RL_OK) return rc;
+  }
+  return RL_OK;
+}
+
 }  // namespace rl
