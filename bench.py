@@ -96,7 +96,7 @@ class ClockSampler:
     def start(self) -> None:
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -104,11 +104,16 @@ class ClockSampler:
         def pump() -> None:
             assert self.proc is not None and self.proc.stdout is not None
             for line in self.proc.stdout:
-                self.lines.append(line.strip())
+                self.lines.append((time.perf_counter(), line.strip()))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self) -> dict:
+    def wait_first_sample(self, timeout: float = 5.0) -> None:
+        t0 = time.perf_counter()
+        while not self.lines and time.perf_counter() - t0 < timeout and self.proc is not None:
+            time.sleep(0.05)
+
+    def stop(self, windows: list[tuple[float, float]] | None = None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -118,7 +123,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for stamp, line in self.lines:
+            if windows and not any(w0 - 0.05 <= stamp <= w1 + 0.15 for w0, w1 in windows):
+                continue
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -274,22 +281,25 @@ def main() -> None:  # noqa: PLR0915
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         out = device_step()
     barrier()
     status = index.last_status.cpu().numpy()
     assert not (status & 1).any(), "candidate overflow in the timed configuration"
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_first_sample()
+    windows = []
     stage_ms = {"prep": 0.0, "sample_scan": 0.0, "select": 0.0, "main_scan": 0.0, "finalize": 0.0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         out = device_step(flags=RL_FLAG_TIME_KERNELS)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    windows.append((w0, time.perf_counter()))
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
@@ -341,6 +351,9 @@ def main() -> None:  # noqa: PLR0915
                                                    exact_maxsim=args.exact_maxsim, algo=args.algo)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    windows.append((t0, t0 + e2e_s))
+    clocks = sampler.stop(windows)
+    clocks["windows"] = "timed device steps + timed e2e steps"
     t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -58,9 +58,9 @@ int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes
 
 /* ---- Index build -------------------------------------------------------------------------
  * Per-row statistics of the embedding matrix E[n_rows, d] (row stride ld floats): inv_norm[j] =
- * 1/|e_j| (0 for a zero row), sq_norm[j] = |e_j|^2, and the global max row norm / max |element|
- * (stats[0], stats[1]; device floats, must be zeroed by the caller) used to scale rows for the
- * fp16 scan.  Replaces nothing in the reference (DuckDB recomputes norms per query inside
+ * 1/|e_j| (0 for a zero row), sq_norm[j] = |e_j|^2, and four global statistics used to scale rows for
+ * the fp16 scan (stats[4], device floats, must be zeroed by the caller): [0] max row norm, [1] max
+ * |element|, [2] max 1/|e_j| over non-zero rows, [3] 1 if any row is all-zero.  Replaces nothing in the reference (DuckDB recomputes norms per query inside
  * array_cosine_distance); it is the device-side part of building the resident index from the
  * chunk_embedding table (_database.py:403-430). */
 int rl_row_stats(const float* E, int64_t n_rows, int d, int64_t ld, float* inv_norm, float* sq_norm,

@@ -128,7 +128,7 @@ class CorpusIndex:
         with torch.cuda.device(self.device):
             self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
             self.sq_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
-            self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+            self.stats = torch.zeros(4, dtype=torch.float32, device=self.device)
             self.row_chunk = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
             off_dev = torch.from_numpy(self.chunk_off).to(self.device)
             check(self.lib.rl_row_stats(_ptr(self.E), self.n_rows, self.d, self.d, _ptr(self.inv_norm),

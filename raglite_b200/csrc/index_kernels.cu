@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
-  float max_norm = 0.f, max_abs = 0.f;
+  float max_norm = 0.f, max_abs = 0.f, max_inv = 0.f;
+  bool zero_row = false;
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const float* row = E + r * ld;
     double s = 0.0;
@@ -55,11 +56,15 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
       sq_norm[r] = (float)s;
       max_norm = fmaxf(max_norm, nrm);
       max_abs = fmaxf(max_abs, ma);
+      if (s > 0.0) max_inv = fmaxf(max_inv, (float)(1.0 / sqrt(s)));
+      else zero_row = true;
     }
   }
   if (lane == 0 && stats != nullptr) {  // non-negative floats order like their int bit patterns
     atomicMax(reinterpret_cast<int*>(stats + 0), __float_as_int(max_norm));
     atomicMax(reinterpret_cast<int*>(stats + 1), __float_as_int(max_abs));
+    atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(max_inv));
+    if (zero_row) atomicMax(reinterpret_cast<int*>(stats + 3), __float_as_int(1.f));
   }
 }
 

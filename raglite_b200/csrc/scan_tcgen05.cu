@@ -36,6 +36,8 @@ constexpr int kThreads = (kFirstLoaderWarp + kNumLoaderWarps) * 32;  // 448
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;  // 16 KB per stage
 constexpr uint32_t kSmemBudget = 222 * 1024;
+constexpr int kPrefetchItems = 6;      // L2 prefetch distance in K-slice items (6 x 32 KB per SM)
+constexpr int kListCap = 768;          // staged hit records per tile before falling back to direct emits
 
 struct TcArgs {
   ScanArgs a;
@@ -127,6 +129,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// v[j] for a run-time j without spilling v to local memory: 31 selects.
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+// Named barrier shared by the 4 epilogue warps only.
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -161,17 +179,24 @@ struct SmemLayout {
   uint32_t* tmem_ptr;
   float* thr;                 // [kMaxQ]
   float* cs;                  // [kMaxQ]
+  int* cnt;                   // [kMaxQ] hits per query staged since the last flush
+  int* basev;                 // [kMaxQ] global slot base per query for the current flush
+  int* list_n;                // [2] number of staged records (ping-pong by tile parity)
+  uint32_t* list;             // [kListCap][3] {col | rank << 16, key bits, row}
 };
 
 __host__ __device__ inline uint32_t stage_bytes(int nq) { return kABytes + (uint32_t)nq * 128u; }
-__host__ __device__ inline uint32_t tail_bytes() { return (2 * kMaxStages + 4) * 8 + 16 + 2 * kMaxQ * 4; }
+__host__ __device__ inline uint32_t tail_bytes() {
+  return (2 * kMaxStages + 4) * 8 + 16 + 4 * kMaxQ * 4 + 16 + kListCap * 12;
+}
 
 template <int METRIC>
-__global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs t) {
+__global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   const ScanArgs& a = t.a;
   // 1024-byte alignment for the 128B-swizzled tiles.
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const uint32_t sbytes = stage_bytes(t.nq);
   SmemLayout s;
   s.stage_base = base;
@@ -182,6 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
   s.thr = reinterpret_cast<float*>(s.tmem_ptr + 4);
   s.cs = s.thr + kMaxQ;
+  s.cnt = reinterpret_cast<int*>(s.cs + kMaxQ);
+  s.basev = s.cnt + kMaxQ;
+  s.list_n = s.basev + kMaxQ;
+  s.list = reinterpret_cast<uint32_t*>(s.list_n + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = a.n_mode_blocks;
@@ -202,12 +231,18 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
   for (int i = threadIdx.x; i < kMaxQ; i += blockDim.x) {
     s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
     s.cs[i] = (i < a.B) ? t.q_scale[i] : 0.f;
+    s.cnt[i] = 0;
   }
+  if (threadIdx.x == 0) { s.list_n[0] = 0; s.list_n[1] = 0; }
   if (warp == kMmaWarp) tmem_alloc(s.tmem_ptr, (uint32_t)t.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_ptr;
+  // Cosine on a corpus whose rows all have norm >= 0.5 and moderate magnitudes (the normal case:
+  // embeddings are stored normalised): rows go to fp16 unscaled and the epilogue applies 1/|e|.
+  const bool cos_noscale = METRIC == RL_METRIC_COSINE && t.row_stats[2] > 0.f && t.row_stats[2] <= 2.f &&
+                           t.row_stats[1] <= 1024.f && t.row_stats[3] == 0.f;
 
   if (warp >= kFirstLoaderWarp) {
     // ===== corpus loaders: HBM fp32 -> registers -> fp16 -> swizzled smem (UMMA A operand) =====
@@ -215,89 +250,175 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
     const int c4 = lt & 15;                              // float4 column within the 64-wide K slice
     const int r0 = lt >> 4;                              // rows r0 + 16 i, i = 0..7
     const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
+    // Rows are converted without a multiply when no scaling is needed (normalised corpora: the
+    // cosine 1/|e| then moves to the epilogue, which has slack; dot/l2: the global scale is 1).
+    const bool noscale = (METRIC == RL_METRIC_COSINE) ? cos_noscale : (gscale == 1.f);
     const int64_t total_items = my_tiles * t.n_ks;
-    float4 cur[8], nxt[8];
+    float4 ring[2][8];
     float rs[8];
 
-    auto issue = [&](int64_t item, float4 (&buf)[8]) {
-      const int64_t tile = item / t.n_ks;
-      const int ks = (int)(item - tile * t.n_ks);
-      const int64_t blk = mode_block_index(a, first + tile * stride);
-      const int col = ks * kSliceK + c4 * 4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = blk * kTileM + r0 + 16 * i;
-        if (row < a.n_rows && col < a.d) buf[i] = ldg_stream(a.E + row * a.ld + col);
-        else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Incremental cursors (no integer divisions or multiplies on the hot path).  `ld_*` runs two items
+    // ahead of `st_*`; `pf_*` runs kPrefetchItems ahead of `ld_*` and only touches L2.
+    const size_t pitch16_bytes = (size_t)a.ld * 16 * sizeof(float);   // between this thread's consecutive rows
+    const size_t slice_bytes = kSliceK * sizeof(float);
+    int64_t ld_tile = 0;
+    int ld_ks = 0, ld_rows = 0;
+    const unsigned char* ld_ptr = nullptr;                 // row r0 of the tile, column c4*4 + ld_ks*64
+    auto ld_set_tile = [&]() {
+      if (ld_tile < my_tiles) {
+        const int64_t blk = mode_block_index(a, first + ld_tile * stride);
+        const int64_t rem = a.n_rows - blk * kTileM;
+        ld_rows = rem < kTileM ? (int)rem : kTileM;
+        ld_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + r0) * a.ld + c4 * 4);
+      } else {
+        ld_rows = 0;
       }
     };
-    auto load_scales = [&](int64_t tile) {
-      const int64_t blk = mode_block_index(a, first + tile * stride);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = blk * kTileM + r0 + 16 * i;
-        rs[i] = (METRIC == RL_METRIC_COSINE) ? (row < a.n_rows ? __ldg(a.inv_norm + row) : 0.f) : gscale;
+    // One 128-byte line per thread and item: thread lt covers row lt/2, half lt%2 of the 256-byte slice.
+    int64_t pf_tile = 0;
+    int pf_ks = 0, pf_rows = 0;
+    const unsigned char* pf_ptr = nullptr;
+    auto pf_set_tile = [&]() {
+      if (pf_tile < my_tiles) {
+        const int64_t blk = mode_block_index(a, first + pf_tile * stride);
+        const int64_t rem = a.n_rows - blk * kTileM;
+        pf_rows = rem < kTileM ? (int)rem : kTileM;
+        pf_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + (lt >> 1)) * a.ld + (lt & 1) * 32);
+        if (METRIC == RL_METRIC_COSINE && lt < 4 && lt * 32 < pf_rows) prefetch_l2(a.inv_norm + blk * kTileM + lt * 32);
+      } else {
+        pf_rows = 0;
       }
+    };
+    auto prefetch_item = [&]() {
+      if ((lt >> 1) < pf_rows && pf_ks * kSliceK + (lt & 1) * 32 < a.d) prefetch_l2(pf_ptr);
+      pf_ptr += slice_bytes;
+      if (++pf_ks == t.n_ks) {
+        pf_ks = 0;
+        ++pf_tile;
+        pf_set_tile();
+      }
+    };
+    auto issue_item = [&](float4 (&buf)[8]) {
+      const bool col_ok = ld_ks * kSliceK + c4 * 4 < a.d;
+      const unsigned char* p = ld_ptr;
+      if (col_ok && ld_rows == kTileM) {   // full tile: no per-row predicates
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          buf[i] = ldg_stream(reinterpret_cast<const float*>(p));
+          p += pitch16_bytes;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (col_ok && r0 + 16 * i < ld_rows) buf[i] = ldg_stream(reinterpret_cast<const float*>(p));
+          else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          p += pitch16_bytes;
+        }
+      }
+      ld_ptr += slice_bytes;
+      if (++ld_ks == t.n_ks) {
+        ld_ks = 0;
+        ++ld_tile;
+        ld_set_tile();
+      }
+      prefetch_item();
     };
 
-    if (total_items > 0) issue(0, cur);
-    for (int64_t item = 0; item < total_items; ++item) {
-      const int ks = (int)(item % t.n_ks);
-      if (ks == 0) load_scales(item / t.n_ks);
-      if (item + 1 < total_items) issue(item + 1, nxt);
-      const int stage = (int)(item % t.stages);
-      const uint32_t phase = (uint32_t)((item / t.stages) & 1);
-      mbar_wait(&s.empty[stage], phase ^ 1u);
-      unsigned char* A = s.stage_base + (size_t)stage * sbytes;
+    int64_t st_tile = 0;
+    int st_ks = 0, stage = 0;
+    uint32_t phase = 0;
+    // Row scales of a tile are (re)loaded right after the last item of the previous tile has been
+    // converted; their latency overlaps the arrive, the next loads and the next barrier wait.
+    auto fetch_scales = [&](int64_t tile) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
-        const __half2 h01 = __floats2half2_rn(cur[i].x * rs[i], cur[i].y * rs[i]);
-        const __half2 h23 = __floats2half2_rn(cur[i].z * rs[i], cur[i].w * rs[i]);
-        uint2 packed;
-        packed.x = *reinterpret_cast<const uint32_t*>(&h01);
-        packed.y = *reinterpret_cast<const uint32_t*>(&h23);
-        // 16-byte chunk j = c4/2 lands at chunk (j ^ (r & 7)); this thread owns half of it.
-        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
-        *reinterpret_cast<uint2*>(A + off) = packed;
+      for (int i = 0; i < 8; ++i) rs[i] = (METRIC == RL_METRIC_COSINE) ? 0.f : gscale;
+      if (METRIC == RL_METRIC_COSINE && !noscale && tile < my_tiles) {
+        const int64_t blk = mode_block_index(a, first + tile * stride);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = blk * kTileM + r0 + 16 * i;
+          if (row < a.n_rows) rs[i] = __ldg(a.inv_norm + row);
+        }
       }
-      fence_proxy_async();  // make the generic-proxy stores visible to the tensor core (async proxy)
+    };
+    // Per-thread constant part of the swizzled store offset: row r = r0 + 16 i has r & 7 == r0 & 7.
+    const uint32_t sw_off = (uint32_t)r0 * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r0 & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+    // Convert + store one item, then refill its register slots with the loads of the item two
+    // ahead: two stage-loads (64 KB per SM) stay in flight.
+    auto process = [&](float4 (&buf)[8]) {
+      mbar_wait(&s.empty[stage], phase ^ 1u);
+      unsigned char* A = s.stage_base + (size_t)stage * sbytes + sw_off;
+      if (noscale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 h01 = __floats2half2_rn(buf[i].x, buf[i].y);
+          const __half2 h23 = __floats2half2_rn(buf[i].z, buf[i].w);
+          uint2 packed;
+          packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+          packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(A + i * 16 * 128) = packed;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 h01 = __floats2half2_rn(buf[i].x * rs[i], buf[i].y * rs[i]);
+          const __half2 h23 = __floats2half2_rn(buf[i].z * rs[i], buf[i].w * rs[i]);
+          uint2 packed;
+          packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+          packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(A + i * 16 * 128) = packed;
+        }
+      }
+      // No proxy fence here: a fence in a thread with global loads in flight stalls until they land and
+      // collapses the loaders' memory-level parallelism.  The stores are released by the mbarrier arrive;
+      // the MMA thread acquires the barrier and executes fence.proxy.async before it issues tcgen05.mma.
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.full[stage]);
-      if (item + 1 < total_items) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-      }
+      issue_item(buf);
+      if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+      if (++st_ks == t.n_ks) { st_ks = 0; ++st_tile; fetch_scales(st_tile); }
+    };
+
+    fetch_scales(0);
+    ld_set_tile();
+    pf_set_tile();
+    for (int i = 0; i < kPrefetchItems; ++i) prefetch_item();
+    issue_item(ring[0]);
+    issue_item(ring[1]);
+    for (int64_t item = 0; item < total_items; item += 2) {
+      process(ring[0]);
+      if (item + 1 < total_items) process(ring[1]);
     }
   } else if (warp == kQWarp) {
     // ===== query producer: bulk-copy the pre-swizzled fp16 K slice of all queries (UMMA B operand) =====
     if (lane == 0) {
       const uint32_t qbytes = (uint32_t)t.nq * 128u;
       const int64_t total_items = my_tiles * t.n_ks;
+      int ks = 0, stage = 0;
+      uint32_t phase = 0;
       for (int64_t item = 0; item < total_items; ++item) {
-        const int ks = (int)(item % t.n_ks);
-        const int stage = (int)(item % t.stages);
-        const uint32_t phase = (uint32_t)((item / t.stages) & 1);
         mbar_wait(&s.empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&s.full[stage], qbytes);
         bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes,
                  reinterpret_cast<const unsigned char*>(t.qimg) + (size_t)ks * qbytes, qbytes, &s.full[stage]);
+        if (++ks == t.n_ks) ks = 0;
+        if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTileM, t.nq);
-      int64_t item = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int64_t tile = 0; tile < my_tiles; ++tile) {
         const int buf = (int)(tile & 1);
         mbar_wait(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * t.buf_cols);
-        for (int ks = 0; ks < t.n_ks; ++ks, ++item) {
-          const int stage = (int)(item % t.stages);
-          const uint32_t phase = (uint32_t)((item / t.stages) & 1);
+        for (int ks = 0; ks < t.n_ks; ++ks) {
           mbar_wait(&s.full[stage], phase);
+          fence_proxy_async();  // generic-proxy smem stores of the loaders -> async proxy (tensor core) reads
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.stage_base + (size_t)stage * sbytes);
           const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
@@ -308,6 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
           }
           umma_commit(&s.empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == t.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&s.tmem_full[buf]);  // accumulator complete -> epilogue
       }
@@ -324,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
       bool valid = row < a.n_rows;
       if (valid && a.row_allowed != nullptr) valid = a.row_allowed[row] != 0;
       const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
+      const float lane_scale = (METRIC == RL_METRIC_COSINE && cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
       mbar_wait(&s.tmem_full[buf], (uint32_t)((tile >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * t.buf_cols);
@@ -337,30 +460,69 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
             if (col < a.B) {
               float key = __uint_as_float(v[j]);
               if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
+              else key *= lane_scale;
               a.dump[(size_t)col * a.n_sample_rows + ord * kTileM + r_in] = valid ? key : kNegInf;
             }
           }
         } else {
-          bool any = false;
+          uint32_t mask = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float key = __uint_as_float(v[j]);
             if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
-            any |= key >= s.thr[c0 + j];
+            else key *= lane_scale;
+            if (key >= s.thr[c0 + j]) mask |= 1u << j;
           }
-          if (any && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float key = __uint_as_float(v[j]);
-              if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
-              if (key >= s.thr[c0 + j]) emit_candidate(a, c0 + j, key, (int32_t)row);
+          if (!valid) mask = 0;
+          while (mask != 0) {  // rare: a few hits per tile; picks v[j] with a register select tree
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            float key = __uint_as_float(select32(v, j));
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
+            else key *= lane_scale;
+            // Stage the hit in shared memory; global slots are claimed once per (tile, query) at the flush.
+            const int pos = atomicAdd(&s.list_n[buf], 1);
+            if (pos < kListCap) {
+              const int rank = atomicAdd(&s.cnt[c0 + j], 1);
+              s.list[pos * 3 + 0] = (uint32_t)(c0 + j) | ((uint32_t)rank << 16);
+              s.list[pos * 3 + 1] = __float_as_uint(key);
+              s.list[pos * 3 + 2] = (uint32_t)row;
+            } else {
+              emit_candidate(a, c0 + j, key, (int32_t)row);
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);
+      if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);  // TMEM buffer is free for tile + 2
+      if (!a.dump_mode) {
+        // Flush the staged hits of this tile: one global atomic per query that was hit.
+        const int et = threadIdx.x;  // 0..127 (epilogue warps are warps 0..3)
+        epi_bar_sync();
+        // The staged-record counter ping-pongs with the tile parity so that a warp running ahead into
+        // the next tile cannot change the count its siblings are about to read.
+        const int n = min(s.list_n[buf], kListCap);
+        if (n > 0) {
+          for (int col = et; col < kMaxQ; col += kNumEpiWarps * 32) {
+            const int c = s.cnt[col];
+            if (c > 0) {
+              s.basev[col] = atomicAdd(a.cand_cnt + col, c);
+              s.cnt[col] = 0;
+            }
+          }
+          epi_bar_sync();
+          if (et == 0) s.list_n[buf] = 0;
+          for (int e = et; e < n; e += kNumEpiWarps * 32) {
+            const uint32_t w0 = s.list[e * 3 + 0];
+            const int col = (int)(w0 & 0xFFFFu);
+            const int slot = s.basev[col] + (int)(w0 >> 16);
+            if (slot < a.cap)
+              a.cand[(size_t)col * a.cap + slot] = Cand{__uint_as_float(s.list[e * 3 + 1]), (int32_t)s.list[e * 3 + 2]};
+          }
+          epi_bar_sync();
+        }
+      }
     }
   }
 

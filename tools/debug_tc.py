@@ -28,6 +28,10 @@ def run(n_chunks, vecs, dim, B, metric="cosine"):
         cols = np.unique(bad[:, 0]); rows = np.unique(bad[:, 1] % 128)
         print("  bad queries:", cols[:20], " bad rows%128:", rows[:40])
 
+if len(sys.argv) > 1 and sys.argv[1] == "stress":
+    for args in [(40000, 8, 1024, 256), (100000, 8, 384, 256), (30000, 12, 1024, 200), (150000, 4, 128, 64)]:
+        run(*args)
+    sys.exit(0)
 for args in [(64, 2, 64, 16), (100, 3, 128, 40), (300, 4, 384, 256), (200, 8, 1024, 128), (500, 2, 100, 7), (400, 4, 64, 300)]:
     run(*args)
 run(300, 2, 64, 16, "dot"); run(300, 2, 64, 16, "l2")
