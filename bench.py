@@ -61,6 +61,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--chunks", type=int, default=0, help="chunks per GPU (override)")
     ap.add_argument("--oversample", type=int, default=4)
     ap.add_argument("--exact-maxsim", action="store_true")
+    ap.add_argument("--adapter", default="auto", choices=["auto", "on", "off"], help="query adapter apply (on for c3)")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
@@ -148,19 +149,24 @@ def cpu_reference_rate(w: dict, sample_chunks: int, reps: int, seed: int = 0) ->
     from oracle.vector_search import blas_batch_topk  # the ONLY product-side use of the oracle: the CPU baseline
     from synth import make_corpus, make_queries
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can.
+    import contextlib
+    want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        from threadpoolctl import threadpool_info, threadpool_limits
+        limiter = threadpool_limits(limits=want)
     except Exception:  # noqa: BLE001
-        threads = os.cpu_count() or 1
+        threadpool_info, limiter = None, contextlib.nullcontext()
     E, _ = make_corpus(sample_chunks, w["vecs"], w["dim"], seed=seed)
     Q = make_queries(E, w["batch"], seed=seed + 1)
-    blas_batch_topk(E[: 1024 * w["vecs"]], w["vecs"], Q[:8], min(w["k"], 64), num_hits=w["num_hits"])  # warm BLAS
     times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        blas_batch_topk(E, w["vecs"], Q, w["k"], num_hits=w["num_hits"])
-        times.append(time.perf_counter() - t0)
+    with limiter:
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1]) if threadpool_info else want
+        blas_batch_topk(E[: 1024 * w["vecs"]], w["vecs"], Q[:8], min(w["k"], 64), num_hits=w["num_hits"])  # warm BLAS
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            blas_batch_topk(E, w["vecs"], Q, w["k"], num_hits=w["num_hits"])
+            times.append(time.perf_counter() - t0)
     t = float(np.median(times))
     raw_qps_sample = w["batch"] / t
     return {"t_sample_s": t, "reps": reps, "threads": int(threads), "sample_chunks": sample_chunks,
@@ -233,6 +239,7 @@ def main() -> None:  # noqa: PLR0915
         run_reference(args, w)
         return
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("RAGLITE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -272,8 +279,14 @@ def main() -> None:  # noqa: PLR0915
     total_chunks = w["chunks"] * world
     norm = total_chunks / TEN_M
 
+    use_adapter = args.adapter == "on" or (args.adapter == "auto" and w["name"] == "c3")
+    if use_adapter:  # orthogonal d x d float64 adapter as the cosine fit produces (_query_adapter.py:204-205)
+        Ad = torch.linalg.svd(torch.randn((d, d), dtype=torch.float64, generator=torch.Generator().manual_seed(2)))
+        local.set_query_adapter((Ad[0] @ Ad[2]).numpy())
+
     def device_step(flags: int = 0):  # noqa: ANN202
-        return index.search_device(Qd, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, checked=False, flags=flags)
+        Qa = local.apply_adapter(Qd, round_fp16=False) if use_adapter else Qd     # _search.py:58-62
+        return index.search_device(Qa, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, checked=False, flags=flags)
 
     def barrier() -> None:
         if world > 1:
@@ -317,6 +330,23 @@ def main() -> None:  # noqa: PLR0915
         for key in stage_ms:
             stage_ms[key] += st[key] / min(5, args.steps)
     scan_ms = float(np.mean(main_ms))
+    comm_ms = None
+    if world > 1:   # where does the multi-GPU step go: scan pipeline vs all-gather vs merge (CUDA events, this rank)
+        from raglite_b200._dist import gather_hits
+        from raglite_b200._index import merge_hits
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = np.zeros(3)
+        for _ in range(5):
+            evs[0].record()
+            res = local.scan(Qd, k=k, num_hits=num_hits, metric="cosine", algo=args.algo)
+            evs[1].record()
+            g = gather_hits(res.hit_sim, res.hit_chunk, res.hit_count, index.group)
+            evs[2].record()
+            merge_hits(*g, num_hits=num_hits, k=k)
+            evs[3].record()
+            torch.cuda.synchronize()
+            acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(3)]) / 5
+        comm_ms = {"scan_pipeline": float(acc[0]), "all_gather": float(acc[1]), "merge": float(acc[2])}
     n_rows = local.n_rows
     S = max(1, stats["sample_stride"])
     n_blocks = (n_rows + 127) // 128
@@ -338,7 +368,7 @@ def main() -> None:  # noqa: PLR0915
                 "tensor_peak_tflops": peaks.get("bf16_tflops")}
 
     # ---- end to end through the public API: host queries in, host results out, every step ----
-    cfg = rl.RAGLiteConfig(db_url=f"bench://rank{rank}", reranker=None, vector_search_query_adapter=False)
+    cfg = rl.RAGLiteConfig(db_url=f"bench://rank{rank}", reranker=None, vector_search_query_adapter=use_adapter)
     rl.register_index(cfg, index)
     Q_np = Q_host.numpy()
     for _ in range(2):
@@ -366,17 +396,18 @@ def main() -> None:  # noqa: PLR0915
         nq = 4
         exact = 0
         sim_err = 0.0
+        Qc = local.apply_adapter(Qd, round_fp16=False) if use_adapter else Qd
         for b in range(nq):
             # fp32 matmul shortlists rows block by block; the shortlist is re-scored in float64.
             take = max(num_hits, k * w["vecs"]) + 64
             short = []
             stepr = 1 << 21
             for r0 in range(0, n_rows, stepr):
-                s = (local.E[r0:r0 + stepr] @ Qd[b]) * local.inv_norm[r0:r0 + stepr]
+                s = (local.E[r0:r0 + stepr] @ Qc[b]) * local.inv_norm[r0:r0 + stepr]
                 short.append(torch.topk(s, min(take, s.numel())).indices + r0)
             rows_c = torch.cat(short)
             e64 = local.E[rows_c].double()
-            s64 = (e64 @ Qd[b].double()) / (e64.norm(dim=1) * Qd[b].double().norm())
+            s64 = (e64 @ Qc[b].double()) / (e64.norm(dim=1) * Qc[b].double().norm())
             o = torch.argsort(s64, descending=True, stable=True)
             if num_hits:
                 o = o[:num_hits]
@@ -401,7 +432,7 @@ def main() -> None:  # noqa: PLR0915
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "chunks_per_gpu": w["chunks"], "vecs_per_chunk": w["vecs"], "dim": d,
-                       "batch": B, "k": k, "num_hits": num_hits, "metric": "cosine",
+                       "batch": B, "k": k, "num_hits": num_hits, "metric": "cosine", "query_adapter": use_adapter,
                        "semantics": "exact MaxSim" if args.exact_maxsim else "reference SQL (top-num_hits vectors -> group max -> top-k)",
                        "chunks_scanned": total_chunks, "normalisation": "value = batch / t_step * chunks_scanned / 10M",
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of per-shard hits" if world > 1 else "single GPU shard",
@@ -410,10 +441,10 @@ def main() -> None:  # noqa: PLR0915
             "e2e": {"value": e2e_value, "unit": "queries/s (10M-chunk equivalent)", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4),
                     "api": "raglite_b200.vector_search_batch (host numpy in -> host numpy out)"},
-            "gpu_launches": int((stats["launches"] + 1) * args.steps),
-            "launches_per_step": {"scan_pipeline": stats["launches"], "merge": 1},
+            "gpu_launches": int((stats["launches"] + 1 + (1 if use_adapter else 0)) * args.steps),
+            "launches_per_step": {"scan_pipeline": stats["launches"], "merge": 1, "adapter_apply": 1 if use_adapter else 0},
             "roofline": roofline,
-            "stage_ms": stage_ms, "last_step_stage_ms": last_stage,
+            "stage_ms": stage_ms, "last_step_stage_ms": last_stage, "multi_gpu_stage_ms": comm_ms,
             "scan_stats": stats, "clocks": clocks, "check": check,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -82,6 +82,60 @@ __device__ float block_kth_largest_lb(int64_t n, int K, Get get, uint32_t* hist,
   return ord2f(((uint32_t)bin1 << 20) | ((uint32_t)bin2 << 8));
 }
 
+// Ascending bitonic sort of n (power of two) keys in shared memory.
+template <class K>
+__device__ void bitonic_sort(K* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const K x = keys[i], y = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+__device__ void bitonic_sort_u64(uint64_t* keys, int n) { bitonic_sort<uint64_t>(keys, n); }
+
+// Cheap lower bound of the K-th largest of a value stream: every thread keeps the T largest values
+// it is handed in registers (one streaming pass, no atomics), the blockDim*T kept values are sorted in
+// shared memory and the K-th largest of that subset is returned (a subset's order statistic never
+// exceeds the full set's).  -inf if K > blockDim*T.  `for_each(cb)` must call cb(value) for every
+// value exactly once across the block.  scratch: blockDim*T words.
+template <int T, class ForEach>
+__device__ float block_topk_lower_bound(ForEach for_each, int K, uint32_t* scratch) {
+  float top[T];
+#pragma unroll
+  for (int i = 0; i < T; ++i) top[i] = kNegInf;
+  for_each([&](float x) {
+    if (x > top[T - 1]) {
+      top[T - 1] = x;
+#pragma unroll
+      for (int j = T - 1; j > 0; --j) {
+        if (top[j] > top[j - 1]) { const float tmp = top[j]; top[j] = top[j - 1]; top[j - 1] = tmp; }
+      }
+    }
+  });
+  const int total = (int)blockDim.x * T;
+#pragma unroll
+  for (int i = 0; i < T; ++i) scratch[threadIdx.x * T + i] = f2ord(top[i]);
+  __syncthreads();
+  bitonic_sort<uint32_t>(scratch, total);   // total is a power of two (512 * {1,4,8})
+  const float lb = K <= total ? ord2f(scratch[total - K]) : kNegInf;
+  __syncthreads();
+  return lb;
+}
+template <class ForEach>
+__device__ float block_topk_lower_bound_any(ForEach for_each, int K, uint32_t* scratch) {
+  if (K <= kSelThreads) return block_topk_lower_bound<1>(for_each, K, scratch);
+  if (K <= 4 * kSelThreads) return block_topk_lower_bound<4>(for_each, K, scratch);
+  return block_topk_lower_bound<8>(for_each, K, scratch);
+}
+
 // ---- query prep ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict__ Q, int B, int d, int metric,
                                                          int algo, const float* __restrict__ row_stats,
@@ -117,47 +171,153 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float* __restrict
 }
 
 // ---- sample select + emit from the dump -----------------------------------------------------------
+constexpr int kSelListCap = 8192;
+
+__device__ __forceinline__ int32_t sample_row_of(int64_t p, int S) {
+  return (int32_t)((p / kBlockRows) * S * kBlockRows + (p % kBlockRows));
+}
+
+// Walk the sampled keys of one query: cb(p, v, sv) with v = the row's approximate key and sv = the
+// value that takes part in the order statistic -- v itself (SQL semantics) or, for exact MaxSim, the
+// max over the run of sample rows one chunk owns, reported once at the head of the run (-inf
+// elsewhere).  A warp owns 32 consecutive sample rows (coalesced loads of keys and owners, kU segments
+// in flight); the run max is a segmented suffix max over the warp (shuffles).  Runs are cut at
+// 32-row segment boundaries: the continuation is not a head, so no chunk is ever counted twice and a
+// partial max only lowers the statistic (it must be a lower bound).
+template <class CB>
+__device__ void for_each_sample(const SelectArgs& a, const float* __restrict__ dump, int64_t n, CB cb) {
+  constexpr int kU = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t n_seg = n / 32;  // n is a multiple of kBlockRows
+  for (int64_t seg0 = (int64_t)warp * kU; seg0 < n_seg; seg0 += (int64_t)nw * kU) {
+    float v[kU];
+    int32_t c[kU], cprev0[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t p = (seg0 + u) * 32 + lane;
+      v[u] = seg0 + u < n_seg ? dump[p] : kNegInf;
+      c[u] = -1 - lane;
+      cprev0[u] = -100;
+      if (!a.mode_sql && seg0 + u < n_seg) {
+        const int64_t row = sample_row_of(p, a.S);
+        if (row < a.n_rows) {
+          c[u] = a.row_chunk[row];
+          // Owner of the row before lane 0: inside the 128-row block, or across blocks when every
+          // block is sampled (S == 1).  Otherwise lane 0 starts a run.
+          if (lane == 0 && row > 0 && ((p % kBlockRows) != 0 || a.S == 1)) cprev0[u] = a.row_chunk[row - 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (seg0 + u >= n_seg) break;
+      const int64_t p = (seg0 + u) * 32 + lane;
+      if (a.mode_sql) {
+        cb(p, v[u], v[u]);
+      } else {
+        int32_t cp = __shfl_up_sync(0xffffffffu, c[u], 1);
+        if (lane == 0) cp = cprev0[u];
+        const bool head = c[u] >= 0 && c[u] != cp;
+        float m = v[u];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float m2 = __shfl_down_sync(0xffffffffu, m, o);
+          const int32_t c2 = __shfl_down_sync(0xffffffffu, c[u], o);
+          if (lane + o < 32 && c2 == c[u]) m = fmaxf(m, m2);
+        }
+        cb(p, v[u], head ? m : kNegInf);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a) {
-  __shared__ uint32_t hist[kBins];
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sel_smem);                   // [kBins] / top-T scratch [4096]
+  Cand* elist = reinterpret_cast<Cand*>(hist + kBins);                      // [kSelListCap] sample rows >= LB - 2 eps
+  float* slist = reinterpret_cast<float*>(elist + kSelListCap);             // [kSelListCap] selection values >= LB
   __shared__ int res[2];
+  __shared__ int n_e, n_s, n_out;
   const int b = blockIdx.x;
   const float* dump = a.dump + (size_t)b * a.n_sample_rows;
   const int64_t n = a.n_sample_rows;
+  const float eps2 = 2.f * a.eps[b];
+
+  // Per-position fallback spelling of the selection value (only used on degenerate inputs).
+  auto sel_value_slow = [&](int64_t p) -> float {
+    if (a.mode_sql) return dump[p];
+    const int r_in = (int)(p % kBlockRows);
+    const int64_t row = sample_row_of(p, a.S);
+    if (row >= a.n_rows) return kNegInf;
+    const int32_t c = a.row_chunk[row];
+    if (row > 0 && (r_in != 0 || a.S == 1) && a.row_chunk[row - 1] == c) return kNegInf;  // not the head of its run
+    float m = dump[p];
+    for (int j = 1; (r_in + j < kBlockRows || a.S == 1) && p + j < n && row + j < a.n_rows && a.row_chunk[row + j] == c; ++j)
+      m = fmaxf(m, dump[p + j]);
+    return m;
+  };
+
+  if (threadIdx.x == 0) { n_e = 0; n_s = 0; n_out = 0; }
+  __syncthreads();
   float thr;
+  bool listed = false;   // elist holds every sample row >= thr
   if (a.reuse_thr) {
     thr = a.thr[b];
   } else {
+    // 1) cheap lower bound LB of the sel_k-th largest selection value
+    const float LB = block_topk_lower_bound_any(
+        [&](auto push) { for_each_sample(a, dump, n, [&](int64_t, float, float sv) { push(sv); }); }, a.sel_k, hist);
+    // 2) one more streaming pass collects the few values at or above the bound
+    const float lo = LB - eps2;
+    for_each_sample(a, dump, n, [&](int64_t p, float v, float sv) {
+      if (v >= lo && v > kNegInf) {
+        const int i = atomicAdd(&n_e, 1);
+        if (i < kSelListCap) elist[i] = Cand{v, sample_row_of(p, a.S)};
+      }
+      if (!a.mode_sql && sv >= LB && sv > kNegInf) {
+        const int i = atomicAdd(&n_s, 1);
+        if (i < kSelListCap) slist[i] = sv;
+      }
+    });
+    __syncthreads();
     float T;
-    if (a.mode_sql) {
-      T = block_kth_largest_lb(n, a.sel_k, [&](int64_t i) { return dump[i]; }, hist, res);
-    } else {
-      // chunk-level: a run of sample positions owned by one chunk contributes its max once
-      auto group_max = [&](int64_t p) -> float {
-        const int64_t blk = (p / kBlockRows) * a.S;
-        const int r_in = (int)(p % kBlockRows);
-        const int64_t row = blk * kBlockRows + r_in;
-        if (row >= a.n_rows) return kNegInf;
-        const int32_t c = a.row_chunk[row];
-        if (r_in != 0 && a.row_chunk[row - 1] == c) return kNegInf;  // not the head of its run
-        float m = dump[p];
-        for (int j = 1; r_in + j < kBlockRows && row + j < a.n_rows && a.row_chunk[row + j] == c; ++j)
-          m = fmaxf(m, dump[p + j]);
-        return m;
-      };
-      T = block_kth_largest_lb(n, a.sel_k, group_max, hist, res);
+    if (LB > kNegInf && n_e <= kSelListCap && n_s <= kSelListCap) {
+      // 3) order statistic over the short list in shared memory
+      if (a.mode_sql) {
+        T = block_kth_largest_lb(n_e, a.sel_k, [&](int64_t i) { const float v = elist[i].key; return v >= LB ? v : kNegInf; }, hist, res);
+      } else {
+        T = block_kth_largest_lb(n_s, a.sel_k, [&](int64_t i) { return slist[i]; }, hist, res);
+      }
+      listed = true;
+    } else {  // degenerate distributions (massive ties, tiny samples): full streaming radix select
+      T = block_kth_largest_lb(n, a.sel_k, sel_value_slow, hist, res);
     }
-    thr = T - 2.f * a.eps[b];
+    thr = T - eps2;
     if (threadIdx.x == 0) a.thr[b] = thr;
   }
-  // Sample rows that pass the threshold join the candidate list like any emitted row.
-  for (int64_t p = threadIdx.x; p < n; p += blockDim.x) {
-    const float v = dump[p];
-    if (v >= thr && v > kNegInf) {
-      const int64_t row = (p / kBlockRows) * a.S * kBlockRows + (p % kBlockRows);
-      const int slot = atomicAdd(a.cand_cnt + b, 1);
-      if (slot < a.cap) a.cand[(size_t)b * a.cap + slot] = Cand{v, (int32_t)row};
+  // Sample rows that pass the threshold join the candidate list like any emitted row.  Nothing else
+  // writes this query's list before the main scan starts, so slots are handed out block-locally.
+  Cand* out = a.cand + (size_t)b * a.cap;
+  if (listed) {
+    const int ne = n_e;
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) {
+      const Cand c = elist[i];
+      if (c.key >= thr) {
+        const int slot = atomicAdd(&n_out, 1);
+        if (slot < a.cap) out[slot] = c;
+      }
+    }
+  } else {
+    for (int64_t p = threadIdx.x; p < n; p += blockDim.x) {
+      const float v = dump[p];
+      if (v >= thr && v > kNegInf) {
+        const int slot = atomicAdd(&n_out, 1);
+        if (slot < a.cap) out[slot] = Cand{v, sample_row_of(p, a.S)};
+      }
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) a.cand_cnt[b] = n_out;
 }
 
 // ---- finalize --------------------------------------------------------------------------------------
@@ -171,23 +331,6 @@ __device__ __forceinline__ float exact_sim(int metric, double dot, double ne, do
   if (metric == RL_METRIC_DOT) return 1.0f - (float)(-dot);
   const double d2 = fmax(0.0, ne + nq - 2.0 * dot);
   return 1.0f - (float)sqrt(d2);
-}
-
-// Ascending bitonic sort of n (power of two) uint64 keys in shared memory.
-__device__ void bitonic_sort_u64(uint64_t* keys, int n) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = keys[i], y = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // flags[i] = 1 when no j < i has the same group id.  O(n^2 / threads); n is a few hundred.
@@ -262,21 +405,63 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
   int st = cnt > f.cap ? RL_STATUS_CAND_OVERFLOW : 0;
   const Cand* cand = f.cand + (size_t)b * f.cap;
 
-  const float T = block_kth_largest_lb(n, f.sel_k, [&](int64_t i) { return cand[i].key; }, hist, res);
-  const float cut = T - 2.f * f.eps[b];
-  if (threadIdx.x == 0) {
-    f.thr_out[b] = cut;
-    s_count = 0;
-  }
+  __shared__ int s_coll;
+  const float eps2 = 2.f * f.eps[b];
+  if (threadIdx.x == 0) { s_count = 0; s_coll = 0; }
   for (int c = threadIdx.x; c < f.d; c += blockDim.x) qv[c] = f.Q[(size_t)b * f.d + c];
+  // 1) cheap lower bound of the sel_k-th largest approximate key (per-thread top-T, no atomics)
+  auto key_of = [&](int64_t i) { return cand[i].key; };
+  auto for_each_cand = [&](auto cb) {   // 4 independent 8-byte loads in flight per thread
+    constexpr int kU = 4;
+    for (int i0 = threadIdx.x; i0 < n; i0 += blockDim.x * kU) {
+      Cand c[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * blockDim.x;
+        c[u] = i < n ? cand[i] : Cand{kNegInf, 0};
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u)
+        if (i0 + u * (int)blockDim.x < n) cb(c[u]);
+    }
+  };
+  const float LB = block_topk_lower_bound_any([&](auto push) { for_each_cand([&](const Cand& c) { push(c.key); }); },
+                                              f.sel_k, hist);
+  // 2) collect the candidates at or above it; the order statistic then runs on that short list
+  const float lo = LB - eps2;
+  for_each_cand([&](const Cand& c) {
+    if (c.key >= lo) {
+      const int pos = atomicAdd(&s_coll, 1);
+      if (pos < RL_MAX_SURVIVORS) keys[pos] = ((uint64_t)f2ord(c.key) << 32) | (uint32_t)c.row;
+    }
+  });
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const Cand c = cand[i];
-    if (c.key >= cut) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < RL_MAX_SURVIVORS) rows[pos] = c.row;
+  const int n_coll = s_coll;
+  float cut;
+  if (LB > kNegInf && n_coll <= RL_MAX_SURVIVORS) {
+    const float T = block_kth_largest_lb(n_coll, f.sel_k, [&](int64_t i) {
+      const float v = ord2f((uint32_t)(keys[i] >> 32));
+      return v >= LB ? v : kNegInf; }, hist, res);
+    cut = T - eps2;
+    for (int i = threadIdx.x; i < n_coll; i += blockDim.x) {
+      const uint64_t kk = keys[i];
+      if (ord2f((uint32_t)(kk >> 32)) >= cut) {
+        const int pos = atomicAdd(&s_count, 1);
+        rows[pos] = (int32_t)(uint32_t)kk;   // pos < n_coll <= RL_MAX_SURVIVORS
+      }
+    }
+  } else {  // degenerate (massive ties / fewer than sel_k candidates): streaming radix select
+    const float T = block_kth_largest_lb(n, f.sel_k, key_of, hist, res);
+    cut = T - eps2;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const Cand c = cand[i];
+      if (c.key >= cut) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < RL_MAX_SURVIVORS) rows[pos] = c.row;
+      }
     }
   }
+  if (threadIdx.x == 0) f.thr_out[b] = cut;
   __syncthreads();
   const int ns_all = s_count;
   const int ns = min(ns_all, RL_MAX_SURVIVORS);
@@ -421,7 +606,9 @@ int launch_query_prep(const float* Q, int B, int d, int metric, int algo, const 
 }
 
 int launch_select(const SelectArgs& a, int B, cudaStream_t stream) {
-  select_kernel<<<B, kSelThreads, 0, stream>>>(a);
+  const size_t smem = (size_t)kBins * 4 + (size_t)kSelListCap * (sizeof(Cand) + sizeof(float));
+  RL_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  select_kernel<<<B, kSelThreads, smem, stream>>>(a);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }
