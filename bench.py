@@ -239,7 +239,10 @@ def main() -> None:  # noqa: PLR0915
         run_reference(args, w)
         return
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("RAGLITE_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # Keep stdout to the one JSON line: library chatter (e.g. "NCCL version ...") goes to stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -454,7 +457,10 @@ def main() -> None:  # noqa: PLR0915
                 "value": r["qps_over_10M"], "unit": "queries/s (10M-chunk equivalent)", "cores": r["threads"], "kind": "port",
                 "sample": f"{sample} chunks ({sample * w['vecs']} vectors) x batch {B}, {r['reps']} reps, median "
                           f"{r['t_sample_s']:.3f} s; extrapolated linearly in vectors"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -163,6 +163,55 @@ int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t*
 int rl_segment_mean_pool(const float* X, int64_t ld, int d, const int32_t* row_begin,
                          const int32_t* row_end, int S, int normalize, uint16_t* out, void* stream);
 
+/* ---- Cross-encoder scoring: _search.py:364-397 (reranker.rank -> FlashRank -> onnxruntime) --------
+ * BERT cross-encoder forward (ms-marco-MiniLM-L-12-v2 architecture: LayerNorm(word+pos+type) ->
+ * n_layers x [self-attention, dense+residual+LN, dense+GELU(erf), dense+residual+LN] -> pooler
+ * (dense+tanh on [CLS]) -> classifier (1 logit)), fp16 storage / fp32 accumulate.  Linear layers are
+ * pre-packed once with rl_xenc_pack_linear into the swizzled fp16 image the tensor-core kernel
+ * bulk-copies.  All pointers are device pointers except `layers` (host array). */
+typedef struct rl_xenc_layer {
+  const void* qkv_img;   /* packed [3H, H]  (Q | K | V rows) */
+  const float* qkv_bias; /* [3H] */
+  const void* o_img;     /* packed [H, H] */
+  const float* o_bias;
+  const float* ln1_g;
+  const float* ln1_b;
+  const void* up_img;    /* packed [F, H] */
+  const float* up_bias;
+  const void* down_img;  /* packed [H, F] */
+  const float* down_bias;
+  const float* ln2_g;
+  const float* ln2_b;
+} rl_xenc_layer;
+
+typedef struct rl_xenc_weights {
+  int32_t n_layers, hidden, n_heads, ffn, vocab, max_pos, type_vocab;
+  float ln_eps;
+  const void* word_emb; /* fp16 [vocab, H] */
+  const void* pos_emb;  /* fp16 [max_pos, H] */
+  const void* type_emb; /* fp16 [type_vocab, H] */
+  const float* emb_ln_g;
+  const float* emb_ln_b;
+  const rl_xenc_layer* layers; /* HOST array of n_layers entries */
+  const float* pooler_w; /* fp32 [H, H] */
+  const float* pooler_b;
+  const float* cls_w;    /* fp32 [H] (num_labels == 1) */
+  const float* cls_b;    /* fp32 [1] */
+} rl_xenc_weights;
+
+size_t rl_xenc_linear_image_bytes(int N, int K);
+/* W[N, K] float32 row-major (torch nn.Linear.weight) -> packed fp16 image. */
+int rl_xenc_pack_linear(const float* W, int N, int K, void* image, void* stream);
+/* Y[T, N] (fp16) = act(X[T, K] (fp16) W^T + bias); act 0 = identity, 1 = GELU(erf). */
+int rl_xenc_linear(const void* X, const void* image, const float* bias, void* Y, int T, int N, int K, int act,
+                   void* stream);
+size_t rl_xenc_workspace_bytes(const rl_xenc_weights* w, int T);
+/* Packed variable-length batch: input_ids/type_ids/pos_ids [T], cu_seqlens [P+1]; max_len = longest
+ * sequence.  out_logit[P], out_score[P] = sigmoid(logit) (FlashRank's score). */
+int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids, const int32_t* type_ids, const int32_t* pos_ids,
+                  const int32_t* cu_seqlens, int P, int T, int max_len, float* out_logit, float* out_score,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

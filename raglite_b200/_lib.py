@@ -23,7 +23,8 @@ RL_MAX_SURVIVORS = 4096
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_chunk_row_map", "rl_adapter_apply",
     "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_copy_dump", "rl_topk_merge",
-    "rl_segment_mean_pool",
+    "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
+    "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
 
 
@@ -47,6 +48,21 @@ class ScanStats(C.Structure):
     ]
 
 
+class XencLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("qkv_img", "qkv_bias", "o_img", "o_bias", "ln1_g", "ln1_b", "up_img", "up_bias",
+                                           "down_img", "down_bias", "ln2_g", "ln2_b")]
+
+
+class XencWeights(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("hidden", C.c_int32), ("n_heads", C.c_int32), ("ffn", C.c_int32), ("vocab", C.c_int32),
+        ("max_pos", C.c_int32), ("type_vocab", C.c_int32), ("ln_eps", C.c_float),
+        ("word_emb", C.c_void_p), ("pos_emb", C.c_void_p), ("type_emb", C.c_void_p), ("emb_ln_g", C.c_void_p),
+        ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(XencLayer)), ("pooler_w", C.c_void_p), ("pooler_b", C.c_void_p),
+        ("cls_w", C.c_void_p), ("cls_b", C.c_void_p),
+    ]
+
+
 _lock = threading.Lock()
 _lib: C.CDLL | None = None
 
@@ -67,8 +83,15 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_maxsim_copy_dump.argtypes = [C.POINTER(ScanParams), vp, vp, C.POINTER(C.c_int64), vp]
     lib.rl_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.rl_segment_mean_pool.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]
+    lib.rl_xenc_linear_image_bytes.argtypes = [i32, i32]
+    lib.rl_xenc_linear_image_bytes.restype = C.c_size_t
+    lib.rl_xenc_pack_linear.argtypes = [vp, i32, i32, vp, vp]
+    lib.rl_xenc_linear.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.rl_xenc_workspace_bytes.argtypes = [C.POINTER(XencWeights), i32]
+    lib.rl_xenc_workspace_bytes.restype = C.c_size_t
+    lib.rl_xenc_score.argtypes = [C.POINTER(XencWeights), vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     for name in EXPORTS:
-        if name not in ("rl_last_error", "rl_maxsim_workspace_bytes"):
+        if name not in ("rl_last_error", "rl_maxsim_workspace_bytes", "rl_xenc_linear_image_bytes", "rl_xenc_workspace_bytes"):
             getattr(lib, name).restype = C.c_int
 
 

@@ -1,0 +1,173 @@
+"""BERT cross-encoder engine on the GPU -- the arithmetic behind ``rerank_chunks``.
+
+The reference calls ``reranker.rank(query=, docs=)`` (``_search.py:395``) on a ``rerankers``
+FlashRankRanker: tokenise (query, passage) pairs, run ms-marco-MiniLM-L-12-v2 (BERT, 12 layers, H=384,
+12 heads, FFN=1536) with onnxruntime, sigmoid the logit, sort.  Here the forward runs in
+``rl_xenc_score`` (hand-written CUDA: tcgen05 linear layers with fused bias/GELU, attention,
+LayerNorm, pooler+classifier) on packed variable-length batches -- no padding tokens are computed.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import XencLayer, XencWeights, check
+
+
+def _stream() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+class CrossEncoderEngine:
+    """Device-resident packed weights + tokenizer + batching."""
+
+    def __init__(self, state_dict: dict[str, torch.Tensor], *, n_layers: int, hidden: int, n_heads: int, ffn: int,
+                 max_pos: int, ln_eps: float = 1e-12, tokenizer: Any | None = None, max_length: int = 512,
+                 device: Any | None = None, max_tokens_per_call: int = 1 << 18) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("raglite_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.tokenizer = tokenizer
+        self.max_length = min(max_length, max_pos)
+        self.max_tokens_per_call = max_tokens_per_call
+        self.hidden, self.n_layers = hidden, n_layers
+        self._keep: list[torch.Tensor] = []
+        sd = {k.removeprefix("bert."): v for k, v in state_dict.items()}
+
+        def f32(name: str) -> torch.Tensor:
+            t = sd[name].detach().to(device=self.device, dtype=torch.float32).contiguous()
+            self._keep.append(t)
+            return t
+
+        def f16(name: str) -> torch.Tensor:
+            t = sd[name].detach().to(device=self.device, dtype=torch.float16).contiguous()
+            self._keep.append(t)
+            return t
+
+        def packed(weight: torch.Tensor) -> torch.Tensor:
+            W = weight.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            N, K = W.shape
+            img = torch.empty(int(self.lib.rl_xenc_linear_image_bytes(N, K)), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                check(self.lib.rl_xenc_pack_linear(W.data_ptr(), N, K, img.data_ptr(), _stream()), "rl_xenc_pack_linear")
+                torch.cuda.current_stream().synchronize()
+            self._keep.append(img)
+            return img
+
+        self._layers = (XencLayer * n_layers)()
+        for l in range(n_layers):
+            pre = f"encoder.layer.{l}."
+            qkv_w = torch.cat([sd[pre + f"attention.self.{n}.weight"] for n in ("query", "key", "value")], dim=0)
+            qkv_b = torch.cat([sd[pre + f"attention.self.{n}.bias"] for n in ("query", "key", "value")], dim=0)
+            qkv_b = qkv_b.detach().to(device=self.device, dtype=torch.float32).contiguous()
+            self._keep.append(qkv_b)
+            L = self._layers[l]
+            L.qkv_img, L.qkv_bias = packed(qkv_w).data_ptr(), qkv_b.data_ptr()
+            L.o_img, L.o_bias = packed(sd[pre + "attention.output.dense.weight"]).data_ptr(), f32(pre + "attention.output.dense.bias").data_ptr()
+            L.ln1_g, L.ln1_b = f32(pre + "attention.output.LayerNorm.weight").data_ptr(), f32(pre + "attention.output.LayerNorm.bias").data_ptr()
+            L.up_img, L.up_bias = packed(sd[pre + "intermediate.dense.weight"]).data_ptr(), f32(pre + "intermediate.dense.bias").data_ptr()
+            L.down_img, L.down_bias = packed(sd[pre + "output.dense.weight"]).data_ptr(), f32(pre + "output.dense.bias").data_ptr()
+            L.ln2_g, L.ln2_b = f32(pre + "output.LayerNorm.weight").data_ptr(), f32(pre + "output.LayerNorm.bias").data_ptr()
+        w = XencWeights()
+        w.n_layers, w.hidden, w.n_heads, w.ffn = n_layers, hidden, n_heads, ffn
+        w.vocab, w.max_pos = int(sd["embeddings.word_embeddings.weight"].shape[0]), max_pos
+        w.type_vocab, w.ln_eps = int(sd["embeddings.token_type_embeddings.weight"].shape[0]), ln_eps
+        w.word_emb = f16("embeddings.word_embeddings.weight").data_ptr()
+        w.pos_emb = f16("embeddings.position_embeddings.weight").data_ptr()
+        w.type_emb = f16("embeddings.token_type_embeddings.weight").data_ptr()
+        w.emb_ln_g, w.emb_ln_b = f32("embeddings.LayerNorm.weight").data_ptr(), f32("embeddings.LayerNorm.bias").data_ptr()
+        w.layers = C.cast(self._layers, C.POINTER(XencLayer))
+        w.pooler_w, w.pooler_b = f32("pooler.dense.weight").data_ptr(), f32("pooler.dense.bias").data_ptr()
+        cls_w = state_dict["classifier.weight"].detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+        if cls_w.numel() != hidden:
+            raise ValueError("only single-logit classifiers (num_labels == 1) are supported")
+        cls_b = state_dict["classifier.bias"].detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self._keep += [cls_w, cls_b]
+        w.cls_w, w.cls_b = cls_w.data_ptr(), cls_b.data_ptr()
+        self.weights = w
+        self._ws: torch.Tensor | None = None
+
+    # ---- constructors ------------------------------------------------------------------------------
+    @classmethod
+    def from_hf(cls, model: Any, tokenizer: Any | None = None, **kw: Any) -> "CrossEncoderEngine":
+        """From a ``transformers.BertForSequenceClassification`` (num_labels == 1)."""
+        c = model.config
+        return cls(model.state_dict(), n_layers=c.num_hidden_layers, hidden=c.hidden_size, n_heads=c.num_attention_heads,
+                   ffn=c.intermediate_size, max_pos=c.max_position_embeddings, ln_eps=c.layer_norm_eps,
+                   tokenizer=tokenizer, **kw)
+
+    @classmethod
+    def from_pretrained(cls, path: Path | str, **kw: Any) -> "CrossEncoderEngine":
+        """Load HF weights + ``tokenizer.json`` from a local directory (no network access is attempted)."""
+        path = Path(path)
+        if not (path / "config.json").exists():
+            raise FileNotFoundError(f"No cross-encoder weights at {path} (expected an HF model directory)")
+        from tokenizers import Tokenizer
+        from transformers import BertForSequenceClassification
+
+        model = BertForSequenceClassification.from_pretrained(path, local_files_only=True)
+        tok = Tokenizer.from_file(str(path / "tokenizer.json")) if (path / "tokenizer.json").exists() else None
+        return cls.from_hf(model, tok, **kw)
+
+    # ---- scoring ---------------------------------------------------------------------------------------
+    def score_tokens(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray]) -> tuple[np.ndarray, np.ndarray]:
+        """Logits and sigmoid scores for already-tokenised pairs (variable lengths, no padding)."""
+        P = len(ids)
+        logits = np.empty(P, np.float32)
+        scores = np.empty(P, np.float32)
+        lens = np.array([len(x) for x in ids], dtype=np.int64)
+        if P and lens.max() > self.max_length:
+            raise ValueError("sequence longer than max_length")
+        start = 0
+        while start < P:
+            end, tok = start, 0
+            while end < P and (end == start or tok + lens[end] <= self.max_tokens_per_call):
+                tok += int(lens[end])
+                end += 1
+            lo, sc = self._score_packed(ids[start:end], type_ids[start:end], lens[start:end])
+            logits[start:end], scores[start:end] = lo, sc
+            start = end
+        return logits, scores
+
+    def _score_packed(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray], lens: np.ndarray
+                      ) -> tuple[np.ndarray, np.ndarray]:
+        P, T = len(ids), int(lens.sum())
+        cu = np.zeros(P + 1, np.int32)
+        cu[1:] = np.cumsum(lens)
+        flat_ids = np.concatenate(ids).astype(np.int32)
+        flat_types = np.concatenate(type_ids).astype(np.int32)
+        flat_pos = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
+        host = torch.from_numpy(np.concatenate([flat_ids, flat_types, flat_pos, cu]))
+        dev = host.to(self.device, non_blocking=True)
+        d_ids, d_types, d_pos, d_cu = dev[:T], dev[T:2 * T], dev[2 * T:3 * T], dev[3 * T:]
+        out = torch.empty((2, P), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            need = int(self.lib.rl_xenc_workspace_bytes(C.byref(self.weights), T))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            check(self.lib.rl_xenc_score(C.byref(self.weights), d_ids.data_ptr(), d_types.data_ptr(), d_pos.data_ptr(),
+                                         d_cu.data_ptr(), P, T, int(lens.max()), out[0].data_ptr(), out[1].data_ptr(),
+                                         self._ws.data_ptr(), self._ws.numel(), _stream()), "rl_xenc_score")
+        res = out.cpu().numpy()
+        return res[0], res[1]
+
+    def encode_pairs(self, queries: Sequence[str], docs: Sequence[str]) -> tuple[list[np.ndarray], list[np.ndarray]]:
+        """[CLS] query [SEP] passage [SEP] with truncation to ``max_length`` (FlashRank's tokenizer setup)."""
+        if self.tokenizer is None:
+            raise ValueError("this engine was built without a tokenizer; use score_tokens")
+        self.tokenizer.enable_truncation(max_length=self.max_length)
+        self.tokenizer.no_padding()
+        enc = self.tokenizer.encode_batch(list(zip(queries, docs, strict=True)))
+        return [np.asarray(e.ids, np.int32) for e in enc], [np.asarray(e.type_ids, np.int32) for e in enc]
+
+    def score_pairs(self, queries: Sequence[str], docs: Sequence[str]) -> list[float]:
+        ids, types = self.encode_pairs(queries, docs)
+        return [float(s) for s in self.score_tokens(ids, types)[1]]
