@@ -361,10 +361,17 @@ def main() -> None:  # noqa: PLR0915
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(w["name"])
+        if tr and w["chunks"] == WORKLOADS[w["name"]]["chunks"] and B == WORKLOADS[w["name"]]["batch"] and not args.exact_maxsim:
+            traffic = tr["traffic_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     flops = 2.0 * B * main_rows * d
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "main scan (emit mode), algo=%s" % {1: "fp32", 2: "tcgen05"}.get(stats["algo"], "?"),
+                "traffic": traffic, "kernel": "main scan (emit mode), algo=%s" % {1: "fp32", 2: "tcgen05"}.get(stats["algo"], "?"),
                 "kernel_ms": scan_ms, "algorithmic_bytes": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "tensor_tflops": flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0,

@@ -40,7 +40,9 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;  // 16 KB per stage
 constexpr uint32_t kSmemBudget = 222 * 1024;
 constexpr int kPrefetchItems = 6;      // L2 prefetch distance in K-slice items (6 x 32 KB per SM)
-constexpr int kListCap = 768;          // staged hit records per tile before falling back to direct emits
+constexpr int kListCap = 2048;         // staged hit records (24 KB)
+constexpr int kFlushAt = 1024;         // flush the staged hits once this many are waiting (or at the end)
+         // staged hit records per tile before falling back to direct emits
 
 struct TcArgs {
   ScanArgs a;
@@ -339,9 +341,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       mbar_wait(&s.tmem_full[buf], (uint32_t)((tile >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * t.buf_cols);
-      for (int c0 = 0; c0 < t.nq; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr0 + (uint32_t)c0, v);
+      // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is processed.
+      auto process_chunk = [&](int c0, const uint32_t (&v)[32]) {
         if (a.dump_mode) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -370,7 +371,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
             else key *= lane_scale;
             // Stage the hit in shared memory; global slots are claimed once per (tile, query) at the flush.
-            const int pos = atomicAdd(&s.list_n[buf], 1);
+            const int pos = atomicAdd(&s.list_n[0], 1);
             if (pos < kListCap) {
               const int rank = atomicAdd(&s.cnt[c0 + j], 1);
               s.list[pos * 3 + 0] = (uint32_t)(c0 + j) | ((uint32_t)rank << 16);
@@ -381,18 +382,34 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             }
           }
         }
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld32_async(taddr0, va);
+      tmem_ld_wait(va);
+      for (int c0 = 0; c0 < t.nq; c0 += 64) {
+        const bool has_b = c0 + 32 < t.nq;
+        if (has_b) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 32), vb);
+        process_chunk(c0, va);
+        if (has_b) {
+          tmem_ld_wait(vb);
+          if (c0 + 64 < t.nq) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 64), va);
+          process_chunk(c0 + 32, vb);
+          if (c0 + 64 < t.nq) tmem_ld_wait(va);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);  // TMEM buffer is free for tile + 2
       if (!a.dump_mode) {
-        // Flush the staged hits of this tile: one global atomic per query that was hit.
+        // Staged hits are flushed when enough have accumulated (or after the last tile): one global
+        // atomic per query that was hit since the previous flush.  The two barriers bracket the read
+        // of the counter so that all 128 epilogue threads take the same decision.
         const int et = threadIdx.x;  // 0..127 (epilogue warps are warps 0..3)
         epi_bar_sync();
-        // The staged-record counter ping-pongs with the tile parity so that a warp running ahead into
-        // the next tile cannot change the count its siblings are about to read.
-        const int n = min(s.list_n[buf], kListCap);
-        if (n > 0) {
+        const int n_all = s.list_n[0];
+        epi_bar_sync();
+        if (n_all >= kFlushAt || (tile + 1 == my_tiles && n_all > 0)) {
+          const int n = min(n_all, kListCap);
           for (int col = et; col < kMaxQ; col += kNumEpiWarps * 32) {
             const int c = s.cnt[col];
             if (c > 0) {
@@ -401,7 +418,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             }
           }
           epi_bar_sync();
-          if (et == 0) s.list_n[buf] = 0;
+          if (et == 0) s.list_n[0] = 0;
           for (int e = et; e < n; e += kNumEpiWarps * 32) {
             const uint32_t w0 = s.list[e * 3 + 0];
             const int col = (int)(w0 & 0xFFFFu);

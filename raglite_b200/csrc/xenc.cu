@@ -33,14 +33,13 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;
 constexpr uint32_t kSmemBudget = 220 * 1024;
 
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
@@ -206,9 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kMaxN);
-      for (int c0 = 0; c0 < nb; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr0 + (uint32_t)c0, v);
+      auto store_chunk = [&](int c0, const uint32_t (&v)[32]) {
         if (row < t.T) {
           uint32_t packed[16];
 #pragma unroll
@@ -219,13 +216,26 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
               x0 = 0.5f * x0 * (1.f + erff(x0 * 0.70710678118654752f));
               x1 = 0.5f * x1 * (1.f + erff(x1 * 0.70710678118654752f));
             }
-            const __half2 h = __floats2half2_rn(x0, x1);
-            packed[jj] = *reinterpret_cast<const uint32_t*>(&h);
+            packed[jj] = pack_half2(x0, x1);
           }
           uint4* dst = reinterpret_cast<uint4*>(t.Y + (size_t)row * t.N + n0 + c0);
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
             dst[jj] = make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
+        }
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld32_async(taddr0, va);
+      tmem_ld_wait(va);
+      for (int c0 = 0; c0 < nb; c0 += 64) {
+        const bool has_b = c0 + 32 < nb;
+        if (has_b) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 32), vb);
+        store_chunk(c0, va);
+        if (has_b) {
+          tmem_ld_wait(vb);
+          if (c0 + 64 < nb) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 64), va);
+          store_chunk(c0 + 32, vb);
+          if (c0 + 64 < nb) tmem_ld_wait(va);
         }
       }
       tc_fence_before();
@@ -255,17 +265,25 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* __restrict
   const __half* ty = type + (size_t)type_ids[tok] * H;
   float x[16];  // H <= 512
   float s = 0.f;
-  int n = 0;
-  for (int c = lane; c < H; c += 32, ++n) {
-    x[n] = __half2float(w[c]) + __half2float(p[c]) + __half2float(ty[c]);
-    s += x[n];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    x[i] = c < H ? __half2float(w[c]) + __half2float(p[c]) + __half2float(ty[c]) : 0.f;
+    s += x[i];
   }
   const float mean = warp_sum_f(s) / (float)H;
   float var = 0.f;
-  for (int i = 0; i < n; ++i) var += (x[i] - mean) * (x[i] - mean);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) var += (x[i] - mean) * (x[i] - mean);
+  }
   const float rstd = rsqrtf(warp_sum_f(var) / (float)H + eps);
-  n = 0;
-  for (int c = lane; c < H; c += 32, ++n) out[(size_t)tok * H + c] = __float2half_rn((x[n] - mean) * rstd * g[c] + bta[c]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) out[(size_t)tok * H + c] = __float2half_rn((x[i] - mean) * rstd * g[c] + bta[c]);
+  }
 }
 
 // out = LayerNorm(x + res), one warp per token.
@@ -277,64 +295,160 @@ __global__ void __launch_bounds__(256) add_ln_kernel(const __half* __restrict__ 
   if (tok >= T) return;
   float x[16];
   float s = 0.f;
-  int n = 0;
-  for (int c = lane; c < H; c += 32, ++n) {
-    x[n] = __half2float(xin[(size_t)tok * H + c]) + __half2float(res[(size_t)tok * H + c]);
-    s += x[n];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    x[i] = c < H ? __half2float(xin[(size_t)tok * H + c]) + __half2float(res[(size_t)tok * H + c]) : 0.f;
+    s += x[i];
   }
   const float mean = warp_sum_f(s) / (float)H;
   float var = 0.f;
-  for (int i = 0; i < n; ++i) var += (x[i] - mean) * (x[i] - mean);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) var += (x[i] - mean) * (x[i] - mean);
+  }
   const float rstd = rsqrtf(warp_sum_f(var) / (float)H + eps);
-  n = 0;
-  for (int c = lane; c < H; c += 32, ++n) out[(size_t)tok * H + c] = __float2half_rn((x[n] - mean) * rstd * g[c] + bta[c]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H) out[(size_t)tok * H + c] = __float2half_rn((x[i] - mean) * rstd * g[c] + bta[c]);
+  }
 }
 
-// ---- attention: one block per (sequence, head); K, V of the head in shared memory, fp32 math ---------------
+// ---- attention: one block per (sequence, head), flash-style on mma.sync tensor cores ---------------------
 // qkv [T, 3H] (Q | K | V), ctx [T, H].  head_dim must be 32 (MiniLM-L12-H384: 12 heads x 32).
+// K and V of the head sit in shared memory (80-byte row pitch: conflict-free ldmatrix); each warp
+// owns 16-query blocks: S = Q K^T with m16n8k16 (fp16 in, fp32 acc), online softmax in the exp2
+// domain, O += P V with P re-packed from the S accumulators as the A operand.
+constexpr int kAttPitch = 40;  // halves
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
 __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
-                                                        int H, int n_heads, float scale, __half* __restrict__ ctx) {
-  extern __shared__ float att_smem[];
+                                                        int H, int n_heads, float scale_log2e, __half* __restrict__ ctx) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
   const int seq = blockIdx.x, head = blockIdx.y;
   const int t0 = cu[seq], L = cu[seq + 1] - t0;
-  float* Ks = att_smem;            // [L][33]
-  float* Vs = Ks + (size_t)L * 33; // [L][33]
-  float* Ps = Vs + (size_t)L * 33; // [4 warps][L]
+  const int Lp = (L + 63) / 64 * 64;
+  __half* Ks = reinterpret_cast<__half*>(att_smem);
+  __half* Vs = Ks + (size_t)Lp * kAttPitch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t ld = (size_t)3 * H;
-  for (int idx = threadIdx.x; idx < L * 32; idx += blockDim.x) {
-    const int j = idx >> 5, d = idx & 31;
-    Ks[j * 33 + d] = __half2float(qkv[(size_t)(t0 + j) * ld + H + head * 32 + d]);
-    Vs[j * 33 + d] = __half2float(qkv[(size_t)(t0 + j) * ld + 2 * H + head * 32 + d]);
+  for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
+    const int j = idx >> 2, c = idx & 3;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+    if (j < L) {
+      const __half* base = qkv + (size_t)(t0 + j) * ld + head * 32 + c * 8;
+      kv = __ldg(reinterpret_cast<const uint4*>(base + H));
+      vv = __ldg(reinterpret_cast<const uint4*>(base + 2 * H));
+    }
+    *reinterpret_cast<uint4*>(Ks + (size_t)j * kAttPitch + c * 8) = kv;
+    *reinterpret_cast<uint4*>(Vs + (size_t)j * kAttPitch + c * 8) = vv;
   }
   __syncthreads();
-  float* P = Ps + (size_t)warp * L;
-  for (int i = warp; i < L; i += 4) {
-    const float qd = __half2float(qkv[(size_t)(t0 + i) * ld + head * 32 + lane]) * scale;
-    float mx = -3.0e38f;
-    for (int j0 = 0; j0 < L; j0 += 32) {
-      const int j = j0 + lane;
-      float sc = 0.f;
+  const int r = lane >> 2, cp = (lane & 3) * 2;
+  for (int qb = warp; qb * 16 < L; qb += 4) {
+    const int q0 = qb * 16 + r, q1 = q0 + 8;
+    uint32_t a[2][4];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        const float qv = __shfl_sync(0xffffffffu, qd, d);
-        if (j < L) sc = fmaf(qv, Ks[j * 33 + d], sc);
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* p0 = qkv + (size_t)(t0 + q0) * ld + head * 32 + ks * 16 + cp;
+      const __half* p1 = qkv + (size_t)(t0 + q1) * ld + head * 32 + ks * 16 + cp;
+      a[ks][0] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0)) : 0u;
+      a[ks][1] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1)) : 0u;
+      a[ks][2] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0 + 8)) : 0u;
+      a[ks][3] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1 + 8)) : 0u;
+    }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float O[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) O[i][e] = 0.f;
+    for (int kb = 0; kb < Lp; kb += 64) {
+      float S[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[j][e] = 0.f;
+        uint32_t b[4];
+        ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
+        mma16816(S[j], a[0], b[0], b[1]);
+        mma16816(S[j], a[1], b[2], b[3]);
       }
-      if (j < L) { P[j] = sc; mx = fmaxf(mx, sc); }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kb + j * 8 + cp + (e & 1);
+          const float v = key < L ? S[j][e] * scale_log2e : -INFINITY;
+          S[j][e] = v;
+          if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every key block holds a valid key
+      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      l0 *= c0; l1 *= c1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { O[i][0] *= c0; O[i][1] *= c0; O[i][2] *= c1; O[i][3] *= c1; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pexp = exp2f(S[j][e] - (e < 2 ? mn0 : mn1));
+          S[j][e] = pexp;
+          if (e < 2) l0 += pexp; else l1 += pexp;
+        }
+      m0 = mn0; m1 = mn1;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(S[2 * kk][0], S[2 * kk][1]);
+        pa[1] = pack_half2(S[2 * kk][2], S[2 * kk][3]);
+        pa[2] = pack_half2(S[2 * kk + 1][0], S[2 * kk + 1][1]);
+        pa[3] = pack_half2(S[2 * kk + 1][2], S[2 * kk + 1][3]);
+#pragma unroll
+        for (int dn2 = 0; dn2 < 2; ++dn2) {
+          uint32_t vb[4];
+          ldsm_x4_trans(vb, Vs + (size_t)(kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kAttPitch +
+                                (dn2 * 2 + (lane >> 4)) * 8);
+          mma16816(O[dn2 * 2], pa, vb[0], vb[1]);
+          mma16816(O[dn2 * 2 + 1], pa, vb[2], vb[3]);
+        }
+      }
     }
-    mx = warp_max_f(mx);
-    float sum = 0.f;
-    for (int j = lane; j < L; j += 32) {
-      const float e = __expf(P[j] - mx);
-      P[j] = e;
-      sum += e;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) {
+      if (q0 < L)
+        *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q0) * H + head * 32 + dn * 8 + cp) = pack_half2(O[dn][0] * inv0, O[dn][1] * inv0);
+      if (q1 < L)
+        *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q1) * H + head * 32 + dn * 8 + cp) = pack_half2(O[dn][2] * inv1, O[dn][3] * inv1);
     }
-    sum = warp_sum_f(sum);
-    __syncwarp();
-    float acc = 0.f;  // lane = output dim
-    for (int j = 0; j < L; ++j) acc = fmaf(P[j], Vs[j * 33 + lane], acc);
-    ctx[(size_t)(t0 + i) * H + head * 32 + lane] = __float2half_rn(acc / sum);
-    __syncwarp();
   }
 }
 
@@ -449,10 +563,10 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
                                                   reinterpret_cast<const __half*>(w->type_emb), w->emb_ln_g, w->emb_ln_b,
                                                   w->ln_eps, T, H, hidden);
   RL_CUDA_CHECK(cudaGetLastError());
-  const size_t att_smem = ((size_t)max_len * 33 * 2 + (size_t)4 * max_len) * sizeof(float);
+  const size_t att_smem = (size_t)((max_len + 63) / 64 * 64) * kAttPitch * 2 * sizeof(__half);
   RL_REQUIRE(att_smem <= 200 * 1024, RL_EUNSUPPORTED, "rl_xenc_score: max_len=%d too long for the attention kernel", max_len);
   RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
-  const float scale = 1.0f / sqrtf(32.f);
+  const float scale = 1.4426950408889634f / sqrtf(32.f);  // softmax in the exp2 domain
   for (int l = 0; l < w->n_layers; ++l) {
     const rl_xenc_layer& L = w->layers[l];
     int rc = launch_linear(hidden, L.qkv_img, L.qkv_bias, qkv, T, 3 * H, H, 0, sms, stream);
