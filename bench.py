@@ -63,6 +63,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--exact-maxsim", action="store_true")
     ap.add_argument("--adapter", default="auto", choices=["auto", "on", "off"], help="query adapter apply (on for c3)")
     ap.add_argument("--algo", default="auto")
+    ap.add_argument("--sample-stride", type=int, default=0, help="override the sampling stride (0 = library heuristic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0)
@@ -289,7 +290,8 @@ def main() -> None:  # noqa: PLR0915
 
     def device_step(flags: int = 0):  # noqa: ANN202
         Qa = local.apply_adapter(Qd, round_fp16=False) if use_adapter else Qd     # _search.py:58-62
-        return index.search_device(Qa, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, checked=False, flags=flags)
+        return index.search_device(Qa, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, checked=False, flags=flags,
+                                   sample_stride=args.sample_stride)
 
     def barrier() -> None:
         if world > 1:
@@ -321,18 +323,13 @@ def main() -> None:  # noqa: PLR0915
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    last_stage = local.kernel_times_ms()          # stage times of the last timed step (CUDA events on the launch stream)
+    # Stage times averaged over the timed steps themselves (CUDA events recorded on the launch stream
+    # inside rl_maxsim_topk; the library keeps a ring of 32 event sets, read after the loop).
+    stage_ms = local.kernel_times_ms()
+    last_stage = dict(stage_ms)
     stats = local.scan_stats()
-
-    # ---- per-kernel roofline: main scan launch, timed live over extra steps ----
-    main_ms = []
-    for _ in range(min(5, args.steps)):
-        device_step(flags=RL_FLAG_TIME_KERNELS)
-        st = local.kernel_times_ms()
-        main_ms.append(st["main_scan"])
-        for key in stage_ms:
-            stage_ms[key] += st[key] / min(5, args.steps)
-    scan_ms = float(np.mean(main_ms))
+    n_rows = local.n_rows
+    scan_ms = float(stage_ms["main_scan"])
     comm_ms = None
     if world > 1:   # where does the multi-GPU step go: scan pipeline vs all-gather vs merge (CUDA events, this rank)
         from raglite_b200._dist import gather_hits
@@ -350,7 +347,6 @@ def main() -> None:  # noqa: PLR0915
             torch.cuda.synchronize()
             acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(3)]) / 5
         comm_ms = {"scan_pipeline": float(acc[0]), "all_gather": float(acc[1]), "merge": float(acc[2])}
-    n_rows = local.n_rows
     S = max(1, stats["sample_stride"])
     n_blocks = (n_rows + 127) // 128
     main_rows = min(n_rows, (n_blocks - (n_blocks + S - 1) // S) * 128)

@@ -133,8 +133,8 @@ typedef struct rl_scan_stats {
 } rl_scan_stats;
 int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream);
 
-/* Device time in ms of the stages of the last rl_maxsim_topk call made with RL_FLAG_TIME_KERNELS on
- * this workspace: ms[0] = prep, ms[1] = sample scan (dump), ms[2] = select, ms[3] = main scan (emit),
+/* Device time in ms of the stages of the rl_maxsim_topk calls made with RL_FLAG_TIME_KERNELS on this
+ * workspace since the previous read (average over up to 32 calls): ms[0] = prep, ms[1] = sample scan (dump), ms[2] = select, ms[3] = main scan (emit),
  * ms[4] = finalize.  CUDA events are recorded on the launching stream; the call synchronises on the
  * last one.  Diagnostics for bench.py's roofline figure. */
 int rl_maxsim_kernel_times(const void* workspace, float* ms);

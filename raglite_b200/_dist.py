@@ -75,12 +75,13 @@ class ShardedIndex:
         self.last_status: torch.Tensor | None = None
 
     def search_device(self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
-                      row_allowed: torch.Tensor | None = None, checked: bool = True, flags: int = 0
-                      ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                      row_allowed: torch.Tensor | None = None, checked: bool = True, flags: int = 0,
+                      sample_stride: int = 0) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Scan the local shard, all-gather, merge.  Everything stays on the device / current stream
         (``checked=True`` adds the host-side overflow check and retry)."""
         fn = self.local.scan_checked if checked else self.local.scan
-        res: ScanResult = fn(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=row_allowed, flags=flags)
+        res: ScanResult = fn(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=row_allowed, flags=flags,
+                             sample_stride=sample_stride)
         self.last_status = res.status
         sim, chunk, count = gather_hits(res.hit_sim, res.hit_chunk, res.hit_count, self.group)
         return merge_hits(sim, chunk, count, num_hits=num_hits, k=k)

@@ -21,24 +21,33 @@ void set_error(const char* fmt, ...) {
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// Stage timing events, keyed by workspace pointer (only touched when RL_FLAG_TIME_KERNELS is set).
+// Stage timing events, keyed by workspace pointer (only touched when RL_FLAG_TIME_KERNELS is set): a ring
+// of event sets, one per timed call, so that a caller can time N back-to-back calls without
+// synchronising in between and read the per-stage average afterwards.
 constexpr int kNumStageEvents = 6;
+constexpr int kEventRing = 32;
 struct StageEvents {
-  cudaEvent_t ev[kNumStageEvents];
+  cudaEvent_t ev[kEventRing][kNumStageEvents];
+  int next = 0;    // set used by the next timed call
+  int count = 0;   // sets recorded since the last read
   bool valid = false;
 };
 static std::mutex g_ev_mutex;
 static std::map<const void*, StageEvents> g_events;
 
-static StageEvents* stage_events_for(const void* ws) {
+static cudaEvent_t* stage_events_for(const void* ws) {
   std::lock_guard<std::mutex> lock(g_ev_mutex);
   StageEvents& se = g_events[ws];
   if (!se.valid) {
-    for (int i = 0; i < kNumStageEvents; ++i)
-      if (cudaEventCreate(&se.ev[i]) != cudaSuccess) return nullptr;
+    for (int r = 0; r < kEventRing; ++r)
+      for (int i = 0; i < kNumStageEvents; ++i)
+        if (cudaEventCreate(&se.ev[r][i]) != cudaSuccess) return nullptr;
     se.valid = true;
   }
-  return &se;
+  cudaEvent_t* set = se.ev[se.next];
+  se.next = (se.next + 1) % kEventRing;
+  if (se.count < kEventRing) ++se.count;
+  return set;
 }
 
 static int floor_pow2(double x) {
@@ -81,7 +90,9 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
     // the main pass then emits (~ sel_k * S per query, 8 bytes each plus select passes).
     const double rows_per_sel = L->mode_sql ? 1.0 : (double)p->max_vecs_per_chunk;
     const double f = std::sqrt((double)L->sel_k * rows_per_sel * 16.0 / ((double)(p->n_rows > 0 ? p->n_rows : 1) * 4.0));
-    S = floor_pow2(f > 0 ? 1.0 / f : 1.0);
+    // The emit pass tightens its thresholds online (histogram refinement), so the sample only has
+    // to seed them: 4x sparser than the static optimum.
+    S = floor_pow2(f > 0 ? 4.0 / f : 1.0);
     if (S > 256) S = 256;
     while (S > 1 && (L->n_blocks / S) * kBlockRows < 8 * (int64_t)(L->sel_k * rows_per_sel)) S /= 2;
     if (L->n_blocks < 64) S = 1;
@@ -94,7 +105,9 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
 
   int64_t cap = p->cand_cap;
   if (cap <= 0) {
-    cap = 4 * sel_final * S + 1024;
+    // ~3-4x sel_final candidates survive the refined thresholds, plus the burst before the first
+    // refresh; the static bound (4 * sel_final * S) only applies to the fp32 scan, which does not refine.
+    cap = algo == RL_ALGO_TCGEN05 ? 32 * sel_final + 8192 : 4 * sel_final * S + 1024;
     if (cap > p->n_rows + 1024) cap = p->n_rows + 1024;
   }
   if (cap < 256) cap = 256;
@@ -115,6 +128,8 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   L->off_qsq = take(B * 8);
   L->off_qscale = take(B * 4);
   L->off_nsurv = take(B * 4);
+  L->off_hist = take(B * kHistBins * 4);
+  L->off_histw = take(B * 4);
   L->off_qimg = take(algo == RL_ALGO_TCGEN05 ? tcgen05_qimg_bytes(p->B, p->d) : 0);
   L->off_dump = take(B * (size_t)L->n_sample_rows * 4);
   L->off_cand = take(B * (size_t)L->cap * sizeof(Cand));
@@ -186,16 +201,19 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   double* q_sq = reinterpret_cast<double*>(ws + L.off_qsq);
   float* q_scale = reinterpret_cast<float*>(ws + L.off_qscale);
   int32_t* n_surv = reinterpret_cast<int32_t*>(ws + L.off_nsurv);
+  int32_t* ghist = reinterpret_cast<int32_t*>(ws + L.off_hist);
+  float* hist_inv_w = reinterpret_cast<float*>(ws + L.off_histw);
   void* qimg = ws + L.off_qimg;
   float* dump = reinterpret_cast<float*>(ws + L.off_dump);
   Cand* cand = reinterpret_cast<Cand*>(ws + L.off_cand);
   const bool reuse = (p->flags & RL_FLAG_REUSE_THRESHOLDS) != 0;
   int launches = 0;
-  StageEvents* se = (p->flags & RL_FLAG_TIME_KERNELS) ? stage_events_for(workspace) : nullptr;
-  auto mark = [&](int i) { if (se) cudaEventRecord(se->ev[i], stream); };
+  cudaEvent_t* se = (p->flags & RL_FLAG_TIME_KERNELS) ? stage_events_for(workspace) : nullptr;
+  auto mark = [&](int i) { if (se) cudaEventRecord(se[i], stream); };
   mark(0);
 
   RL_CUDA_CHECK(cudaMemsetAsync(cand_cnt, 0, (size_t)p->B * 4, stream));
+  RL_CUDA_CHECK(cudaMemsetAsync(ghist, 0, (size_t)p->B * kHistBins * 4, stream));
   rc = launch_query_prep(p->Q, p->B, p->d, p->metric, L.algo, p->row_stats, q_sq, q_inv, eps, stream);
   if (rc != RL_OK) return rc;
   ++launches;
@@ -211,6 +229,8 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   a.Q = p->Q; a.q_inv_norm = q_inv; a.thr = thr; a.dump = dump; a.cand = cand; a.cand_cnt = cand_cnt;
   a.n_rows = p->n_rows; a.ld = p->ld; a.n_sample_rows = L.n_sample_rows;
   a.d = p->d; a.B = p->B; a.metric = p->metric; a.S = L.S; a.cap = L.cap;
+  a.ghist = ghist; a.eps = eps; a.hist_inv_w = hist_inv_w;
+  a.sel_count = L.mode_sql ? p->num_hits : (p->k - 1) * p->max_vecs_per_chunk + 1;
 
   auto scan = [&](int dump_mode, int64_t n_mode_blocks) -> int {
     if (n_mode_blocks == 0) return RL_OK;
@@ -231,6 +251,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   mark(2);
   SelectArgs s;
   s.dump = dump; s.row_chunk = p->row_chunk; s.eps = eps; s.thr = thr; s.cand = cand; s.cand_cnt = cand_cnt;
+  s.ghist = ghist; s.hist_inv_w = hist_inv_w;
   s.n_sample_rows = L.n_sample_rows; s.n_rows = p->n_rows; s.S = L.S; s.cap = L.cap; s.mode_sql = L.mode_sql;
   s.sel_k = L.sel_k; s.reuse_thr = reuse ? 1 : 0;
   rc = launch_select(s, p->B, stream);
@@ -255,16 +276,23 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
 
 extern "C" int rl_maxsim_kernel_times(const void* workspace, float* ms) {
   RL_REQUIRE(workspace && ms, RL_EINVAL, "rl_maxsim_kernel_times: null pointer");
-  StageEvents se;
-  {
-    std::lock_guard<std::mutex> lock(g_ev_mutex);
-    auto it = g_events.find(workspace);
-    RL_REQUIRE(it != g_events.end() && it->second.valid, RL_EINVAL,
-               "rl_maxsim_kernel_times: no timed call on this workspace");
-    se = it->second;
+  std::lock_guard<std::mutex> lock(g_ev_mutex);
+  auto it = g_events.find(workspace);
+  RL_REQUIRE(it != g_events.end() && it->second.valid && it->second.count > 0, RL_EINVAL,
+             "rl_maxsim_kernel_times: no timed call on this workspace");
+  StageEvents& se = it->second;
+  for (int i = 0; i + 1 < kNumStageEvents; ++i) ms[i] = 0.f;
+  const int n = se.count;
+  for (int c = 0; c < n; ++c) {
+    cudaEvent_t* set = se.ev[(se.next - 1 - c + 2 * kEventRing) % kEventRing];
+    RL_CUDA_CHECK(cudaEventSynchronize(set[kNumStageEvents - 1]));
+    for (int i = 0; i + 1 < kNumStageEvents; ++i) {
+      float t = 0.f;
+      RL_CUDA_CHECK(cudaEventElapsedTime(&t, set[i], set[i + 1]));
+      ms[i] += t / (float)n;
+    }
   }
-  RL_CUDA_CHECK(cudaEventSynchronize(se.ev[kNumStageEvents - 1]));
-  for (int i = 0; i + 1 < kNumStageEvents; ++i) RL_CUDA_CHECK(cudaEventElapsedTime(&ms[i], se.ev[i], se.ev[i + 1]));
+  se.count = 0;
   return RL_OK;
 }
 

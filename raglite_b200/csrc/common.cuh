@@ -53,6 +53,16 @@ __host__ __device__ __forceinline__ float ord2f(uint32_t o) {
 #endif
 }
 
+// Online threshold refinement: every emitted candidate is also counted in a small per-query
+// histogram of (key - thr0) in bins of 4 eps; once the count at or above a bin edge reaches the
+// selection size, that edge (minus the 2 eps guard band) is a valid, tighter emission threshold.
+constexpr int kHistBins = 16;
+__host__ __device__ __forceinline__ int hist_bin(float key, float thr0, float inv_w) {
+  const float x = (key - thr0) * inv_w;
+  const int b = x > 0.f ? (int)x : 0;
+  return b < kHistBins - 1 ? b : kHistBins - 1;
+}
+
 // Candidate record emitted by the scan: approximate key + shard-local row.
 struct __align__(8) Cand {
   float key;
@@ -77,7 +87,7 @@ struct Layout {
   int b_pad;             // B rounded up to 16
   // byte offsets
   size_t off_hdr, off_dump, off_cand, off_cnt, off_thr, off_thr_out, off_eps, off_qinv, off_qsq,
-      off_qscale, off_qimg, off_nsurv, total;
+      off_qscale, off_qimg, off_nsurv, off_hist, off_histw, total;
 };
 int make_layout(const rl_scan_params* p, int sm_count, Layout* L);
 

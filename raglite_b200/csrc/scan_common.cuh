@@ -15,6 +15,10 @@ struct ScanArgs {
   float* dump;               // [B, n_sample_rows] (DUMP mode)
   Cand* cand;                // [B, cap]
   int32_t* cand_cnt;         // [B]
+  int32_t* ghist;            // [B, kHistBins] emitted-candidate histogram (online threshold refinement)
+  const float* eps;          // [B] error bound of the approximate key
+  const float* hist_inv_w;   // [B] 1 / histogram bin width (from the select kernel)
+  int32_t sel_count;         // #vectors at/above an edge that make it a valid threshold
   int64_t n_rows, ld, n_sample_rows;
   int64_t n_mode_blocks;     // number of blocks this launch covers
   int32_t d, B, metric, S, cap;

@@ -40,8 +40,10 @@ constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;  // 16 KB per stage
 constexpr uint32_t kSmemBudget = 222 * 1024;
 constexpr int kPrefetchItems = 6;      // L2 prefetch distance in K-slice items (6 x 32 KB per SM)
-constexpr int kListCap = 2048;         // staged hit records (24 KB)
-constexpr int kFlushAt = 1024;         // flush the staged hits once this many are waiting (or at the end)
+constexpr int kListCap = 1024;         // staged hit records (12 KB)
+constexpr int kFlushFirst = 192;       // first flush early: it feeds the histogram that tightens the thresholds
+constexpr int kFlushAt = 512;          // later flushes: once this many hits are waiting (or at the end)
+constexpr int kRefreshEvery = 16;      // tiles between threshold refreshes from the global histogram
          // staged hit records per tile before falling back to direct emits
 
 struct TcArgs {
@@ -70,6 +72,9 @@ struct SmemLayout {
   uint32_t* tmem_ptr;
   float* thr;                 // [kMaxQ]
   float* cs;                  // [kMaxQ]
+  float* thr0;                // [kMaxQ] threshold from the sample (histogram origin)
+  float* inv_w;               // [kMaxQ] 1 / bin width (bin width = 4 eps)
+  uint32_t* hist;             // [kMaxQ * kHistBins / 2] staged histogram, two 16-bit counters per word
   int* cnt;                   // [kMaxQ] hits per query staged since the last flush
   int* basev;                 // [kMaxQ] global slot base per query for the current flush
   int* list_n;                // [2] number of staged records (ping-pong by tile parity)
@@ -78,7 +83,7 @@ struct SmemLayout {
 
 __host__ __device__ inline uint32_t stage_bytes(int nq) { return kABytes + (uint32_t)nq * 128u; }
 __host__ __device__ inline uint32_t tail_bytes() {
-  return (2 * kMaxStages + 4) * 8 + 16 + 4 * kMaxQ * 4 + 16 + kListCap * 12;
+  return (2 * kMaxStages + 4) * 8 + 16 + 6 * kMaxQ * 4 + kMaxQ * kHistBins * 2 + 16 + kListCap * 12;
 }
 
 template <int METRIC>
@@ -98,7 +103,10 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
   s.thr = reinterpret_cast<float*>(s.tmem_ptr + 4);
   s.cs = s.thr + kMaxQ;
-  s.cnt = reinterpret_cast<int*>(s.cs + kMaxQ);
+  s.thr0 = s.cs + kMaxQ;
+  s.inv_w = s.thr0 + kMaxQ;
+  s.hist = reinterpret_cast<uint32_t*>(s.inv_w + kMaxQ);
+  s.cnt = reinterpret_cast<int*>(s.hist + kMaxQ * kHistBins / 2);
   s.basev = s.cnt + kMaxQ;
   s.list_n = s.basev + kMaxQ;
   s.list = reinterpret_cast<uint32_t*>(s.list_n + 4);
@@ -123,7 +131,10 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
     s.cs[i] = (i < a.B) ? t.q_scale[i] : 0.f;
     s.cnt[i] = 0;
+    s.thr0[i] = s.thr[i];
+    s.inv_w[i] = (i < a.B && !a.dump_mode) ? a.hist_inv_w[i] : 0.f;
   }
+  for (int i = threadIdx.x; i < kMaxQ * kHistBins / 2; i += blockDim.x) s.hist[i] = 0u;
   if (threadIdx.x == 0) { s.list_n[0] = 0; s.list_n[1] = 0; }
   if (warp == kMmaWarp) tmem_alloc(s.tmem_ptr, (uint32_t)t.tmem_cols);
   tc_fence_before();
@@ -328,6 +339,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   } else {
     // ===== epilogue warps 0..3: TMEM -> registers -> key -> dump / threshold + emit =====
     const int q = warp;  // TMEM lane quarter
+    bool flushed_once = false;
     for (int64_t tile = 0; tile < my_tiles; ++tile) {
       const int buf = (int)(tile & 1);
       const int64_t ord = first + tile * stride;
@@ -372,6 +384,10 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             else key *= lane_scale;
             // Stage the hit in shared memory; global slots are claimed once per (tile, query) at the flush.
             const int pos = atomicAdd(&s.list_n[0], 1);
+            {
+              const int hb = (c0 + j) * kHistBins + hist_bin(key, s.thr0[c0 + j], s.inv_w[c0 + j]);
+              atomicAdd(&s.hist[hb >> 1], 1u << ((hb & 1) * 16));
+            }
             if (pos < kListCap) {
               const int rank = atomicAdd(&s.cnt[c0 + j], 1);
               s.list[pos * 3 + 0] = (uint32_t)(c0 + j) | ((uint32_t)rank << 16);
@@ -402,19 +418,30 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);  // TMEM buffer is free for tile + 2
       if (!a.dump_mode) {
         // Staged hits are flushed when enough have accumulated (or after the last tile): one global
-        // atomic per query that was hit since the previous flush.  The two barriers bracket the read
-        // of the counter so that all 128 epilogue threads take the same decision.
+        // atomic per query that was hit since the previous flush, plus the staged histogram.  The two
+        // barriers bracket the read of the counter so that all 128 epilogue threads decide alike.
         const int et = threadIdx.x;  // 0..127 (epilogue warps are warps 0..3)
         epi_bar_sync();
         const int n_all = s.list_n[0];
         epi_bar_sync();
-        if (n_all >= kFlushAt || (tile + 1 == my_tiles && n_all > 0)) {
+        const bool last = tile + 1 == my_tiles;
+        const bool do_flush = n_all >= (flushed_once ? kFlushAt : kFlushFirst) || (last && n_all > 0);
+        if (do_flush) {
+          flushed_once = true;
           const int n = min(n_all, kListCap);
           for (int col = et; col < kMaxQ; col += kNumEpiWarps * 32) {
             const int c = s.cnt[col];
             if (c > 0) {
               s.basev[col] = atomicAdd(a.cand_cnt + col, c);
               s.cnt[col] = 0;
+            }
+          }
+          for (int w = et; w < kMaxQ * kHistBins / 2; w += kNumEpiWarps * 32) {
+            const uint32_t h = s.hist[w];
+            if (h != 0u) {
+              if (h & 0xFFFFu) atomicAdd(a.ghist + 2 * w, (int)(h & 0xFFFFu));
+              if (h >> 16) atomicAdd(a.ghist + 2 * w + 1, (int)(h >> 16));
+              s.hist[w] = 0u;
             }
           }
           epi_bar_sync();
@@ -426,8 +453,34 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             if (slot < a.cap)
               a.cand[(size_t)col * a.cap + slot] = Cand{__uint_as_float(s.list[e * 3 + 1]), (int32_t)s.list[e * 3 + 2]};
           }
-          epi_bar_sync();
         }
+        if ((do_flush || (tile % kRefreshEvery) == kRefreshEvery - 1) && !last) {
+          // Threshold refresh: the highest bin edge with >= sel_count candidates at or above it (all
+          // CTAs' hits so far) bounds the sel_count-th best key from below; emit from 2 eps under it.
+          for (int col = et; col < a.B; col += kNumEpiWarps * 32) {
+            const int4* gh = reinterpret_cast<const int4*>(a.ghist + (size_t)col * kHistBins);
+            int cnts[kHistBins];
+#pragma unroll
+            for (int q4 = 0; q4 < kHistBins / 4; ++q4) {
+              const int4 v4 = __ldcg(gh + q4);
+              cnts[4 * q4] = v4.x; cnts[4 * q4 + 1] = v4.y; cnts[4 * q4 + 2] = v4.z; cnts[4 * q4 + 3] = v4.w;
+            }
+            int cum = 0, best = -1;
+#pragma unroll
+            for (int bb = kHistBins - 1; bb >= 1; --bb) {
+              cum += cnts[bb];
+              if (best < 0 && cum >= a.sel_count) best = bb;
+            }
+            if (best >= 1) {
+              // edge = thr0 + best * w; new emission threshold = edge - 2 eps
+              if (s.inv_w[col] > 0.f) {
+                const float nt = s.thr0[col] + (float)best / s.inv_w[col] - 2.f * a.eps[col];
+                if (nt > s.thr[col]) s.thr[col] = nt;
+              }
+            }
+          }
+        }
+        if (do_flush || (tile % kRefreshEvery) == kRefreshEvery - 1) epi_bar_sync();
       }
     }
   }
@@ -517,6 +570,9 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.a.dump = a_in.dump + (size_t)q0 * a_in.n_sample_rows;
     t.a.cand = a_in.cand + (size_t)q0 * a_in.cap;
     t.a.cand_cnt = a_in.cand_cnt + q0;
+    t.a.ghist = a_in.ghist + (size_t)q0 * kHistBins;
+    t.a.eps = a_in.eps + q0;
+    t.a.hist_inv_w = a_in.hist_inv_w + q0;
     t.a.q_inv_norm = a_in.q_inv_norm + q0;
     t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g * n_ks * kMaxQ * kSliceK;
     t.q_scale = q_scale + q0;

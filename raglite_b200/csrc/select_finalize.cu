@@ -260,9 +260,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
   if (threadIdx.x == 0) { n_e = 0; n_s = 0; n_out = 0; }
   __syncthreads();
   float thr;
+  float inv_w = eps2 > 0.f ? 1.f / (2.f * eps2) : 0.f;   // default bin width 4 eps
   bool listed = false;   // elist holds every sample row >= thr
   if (a.reuse_thr) {
     thr = a.thr[b];
+    if (threadIdx.x == 0) a.hist_inv_w[b] = inv_w;
   } else {
     // 1) cheap lower bound LB of the sel_k-th largest selection value
     const float LB = block_topk_lower_bound_any(
@@ -293,11 +295,34 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
       T = block_kth_largest_lb(n, a.sel_k, sel_value_slow, hist, res);
     }
     thr = T - eps2;
-    if (threadIdx.x == 0) a.thr[b] = thr;
+    // Histogram bin width for the online refinement.  The tail of the score distribution is roughly
+    // exponential: with T2 = the (sel_k/4)-th largest sample value, (T2 - T) / ln 4 estimates its decay
+    // length, and the shard-wide sel_k-th largest sits about ln(S) decay lengths above T.  Spread the
+    // bins over 1.5x that distance (an outlier-proof estimate: single planted neighbours do not move it).
+    float w = 2.f * eps2;   // 4 eps
+    if (listed && a.S > 1) {
+      const int k2 = max(1, a.sel_k / 4);
+      float T2;
+      if (a.mode_sql) {
+        T2 = block_kth_largest_lb(n_e, k2, [&](int64_t i) { return elist[i].key; }, hist, res);
+      } else {
+        T2 = block_kth_largest_lb(n_s, k2, [&](int64_t i) { return slist[i]; }, hist, res);
+      }
+      if (T2 > T) {
+        const float gap = (T2 - T) * (__logf((float)a.S) / __logf((float)(a.sel_k >= 4 ? 4 : a.sel_k + 1)));
+        w = fmaxf(w, 1.5f * gap / (float)(kHistBins - 1));
+      }
+    }
+    inv_w = w > 0.f ? 1.f / w : 0.f;
+    if (threadIdx.x == 0) {
+      a.thr[b] = thr;
+      a.hist_inv_w[b] = inv_w;
+    }
   }
   // Sample rows that pass the threshold join the candidate list like any emitted row.  Nothing else
   // writes this query's list before the main scan starts, so slots are handed out block-locally.
   Cand* out = a.cand + (size_t)b * a.cap;
+  int32_t* gh = a.ghist + (size_t)b * kHistBins;
   if (listed) {
     const int ne = n_e;
     for (int i = threadIdx.x; i < ne; i += blockDim.x) {
@@ -305,6 +330,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
       if (c.key >= thr) {
         const int slot = atomicAdd(&n_out, 1);
         if (slot < a.cap) out[slot] = c;
+        atomicAdd(gh + hist_bin(c.key, thr, inv_w), 1);
       }
     }
   } else {
@@ -313,6 +339,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectArgs a)
       if (v >= thr && v > kNegInf) {
         const int slot = atomicAdd(&n_out, 1);
         if (slot < a.cap) out[slot] = Cand{v, sample_row_of(p, a.S)};
+        atomicAdd(gh + hist_bin(v, thr, inv_w), 1);
       }
     }
   }

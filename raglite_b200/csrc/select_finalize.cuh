@@ -11,6 +11,8 @@ struct SelectArgs {
   float* thr;                 // [B] in/out
   Cand* cand;                 // [B, cap]
   int32_t* cand_cnt;          // [B]
+  int32_t* ghist;             // [B, kHistBins]
+  float* hist_inv_w;          // [B] out: 1 / histogram bin width chosen from the sample
   int64_t n_sample_rows, n_rows;
   int32_t S, cap, mode_sql, sel_k, reuse_thr;
 };
