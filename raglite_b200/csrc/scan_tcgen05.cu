@@ -18,6 +18,8 @@
 // All hand-offs are mbarrier based (full/empty per smem stage, full/empty per TMEM buffer).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "scan_tcgen05.cuh"
 #include "tcgen05_ptx.cuh"
 
@@ -86,14 +88,16 @@ __host__ __device__ inline uint32_t tail_bytes() {
   return (2 * kMaxStages + 4) * 8 + 16 + 6 * kMaxQ * 4 + kMaxQ * kHistBins * 2 + 16 + kListCap * 12;
 }
 
-template <int METRIC>
+// PAIR: two CTAs of a cluster (an SM pair) issue one cta_group::2 MMA (M = 256: 128 rows per CTA) and
+// each holds only half of the queries in shared memory, which halves the L2 -> SM query stream.
+template <int METRIC, bool PAIR>
 __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   const ScanArgs& a = t.a;
   // 1024-byte alignment for the 128B-swizzled tiles.
   // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const uint32_t sbytes = stage_bytes(t.nq);
+  const uint32_t sbytes = stage_bytes(PAIR ? t.nq / 2 : t.nq);
   SmemLayout s;
   s.stage_base = base;
   s.full = reinterpret_cast<uint64_t*>(base + (size_t)t.stages * sbytes);
@@ -112,18 +116,27 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   s.list = reinterpret_cast<uint32_t*>(s.list_n + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_tiles = a.n_mode_blocks;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
+  // Work units: blocks of 128 rows (single CTA) or pairs of consecutive block ordinals (PAIR: CTA
+  // `rank` of the cluster takes ordinal 2 * unit + rank; a missing second block is an empty tile).
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int64_t n_tiles = PAIR ? (a.n_mode_blocks + 1) / 2 : a.n_mode_blocks;
+  const int64_t first = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t stride = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   const int64_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  auto ord_of = [&](int64_t tile) -> int64_t {
+    const int64_t unit = first + tile * stride;
+    return PAIR ? 2 * unit + rank : unit;
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < t.stages; ++i) {
-      mbar_init(&s.full[i], kNumLoaderWarps + 1);  // 8 loader warps + the query producer (expect_tx)
+      // 8 loader warps + the query producer (expect_tx) [+ the peer CTA's relay in the leader]
+      mbar_init(&s.full[i], kNumLoaderWarps + 1 + ((PAIR && rank == 0) ? 1 : 0));
       mbar_init(&s.empty[i], 1);                   // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s.tmem_full[i], 1);
-      mbar_init(&s.tmem_empty[i], kNumEpiWarps);
+      mbar_init(&s.tmem_empty[i], PAIR ? 2 * kNumEpiWarps : kNumEpiWarps);  // PAIR: both CTAs' epilogues
     }
     fence_barrier_init();
   }
@@ -136,9 +149,13 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   }
   for (int i = threadIdx.x; i < kMaxQ * kHistBins / 2; i += blockDim.x) s.hist[i] = 0u;
   if (threadIdx.x == 0) { s.list_n[0] = 0; s.list_n[1] = 0; }
-  if (warp == kMmaWarp) tmem_alloc(s.tmem_ptr, (uint32_t)t.tmem_cols);
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_alloc_2cta(s.tmem_ptr, (uint32_t)t.tmem_cols);
+    else tmem_alloc(s.tmem_ptr, (uint32_t)t.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_ptr;
   // Cosine on a corpus whose rows all have norm >= 0.5 and moderate magnitudes (the normal case:
@@ -167,8 +184,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int ld_ks = 0, ld_rows = 0;
     const unsigned char* ld_ptr = nullptr;                 // row r0 of the tile, column c4*4 + ld_ks*64
     auto ld_set_tile = [&]() {
-      if (ld_tile < my_tiles) {
-        const int64_t blk = mode_block_index(a, first + ld_tile * stride);
+      if (ld_tile < my_tiles && ord_of(ld_tile) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(ld_tile));
         const int64_t rem = a.n_rows - blk * kTileM;
         ld_rows = rem < kTileM ? (int)rem : kTileM;
         ld_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + r0) * a.ld + c4 * 4);
@@ -181,8 +198,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int pf_ks = 0, pf_rows = 0;
     const unsigned char* pf_ptr = nullptr;
     auto pf_set_tile = [&]() {
-      if (pf_tile < my_tiles) {
-        const int64_t blk = mode_block_index(a, first + pf_tile * stride);
+      if (pf_tile < my_tiles && ord_of(pf_tile) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(pf_tile));
         const int64_t rem = a.n_rows - blk * kTileM;
         pf_rows = rem < kTileM ? (int)rem : kTileM;
         pf_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + (lt >> 1)) * a.ld + (lt & 1) * 32);
@@ -234,8 +251,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     auto fetch_scales = [&](int64_t tile) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) rs[i] = (METRIC == RL_METRIC_COSINE) ? 0.f : gscale;
-      if (METRIC == RL_METRIC_COSINE && !noscale && tile < my_tiles) {
-        const int64_t blk = mode_block_index(a, first + tile * stride);
+      if (METRIC == RL_METRIC_COSINE && !noscale && tile < my_tiles && ord_of(tile) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(tile));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int64_t row = blk * kTileM + r0 + 16 * i;
@@ -294,32 +311,50 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   } else if (warp == kQWarp) {
     // ===== query producer: bulk-copy the pre-swizzled fp16 K slice of all queries (UMMA B operand) =====
     if (lane == 0) {
-      const uint32_t qbytes = (uint32_t)t.nq * 128u;
+      const uint32_t slice_bytes_q = (uint32_t)t.nq * 128u;                 // one K slice of all queries
+      const uint32_t qbytes = PAIR ? slice_bytes_q / 2 : slice_bytes_q;     // PAIR: this CTA's half of the queries
+      const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(t.qimg) + (PAIR ? (size_t)rank * qbytes : 0);
       const int64_t total_items = my_tiles * t.n_ks;
       int ks = 0, stage = 0;
       uint32_t phase = 0;
       for (int64_t item = 0; item < total_items; ++item) {
         mbar_wait(&s.empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&s.full[stage], qbytes);
-        bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes,
-                 reinterpret_cast<const unsigned char*>(t.qimg) + (size_t)ks * qbytes, qbytes, &s.full[stage]);
+        bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes, qsrc + (size_t)ks * slice_bytes_q, qbytes,
+                 &s.full[stage]);
         if (++ks == t.n_ks) ks = 0;
         if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer: one thread drives the tensor core =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, t.nq);
+    if (PAIR && rank != 0) {
+      // Peer CTA: no MMA issue.  Relay "my A tile and my half of the queries are in place" to the
+      // leader's full barrier, stage by stage.
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int64_t total_items = my_tiles * t.n_ks;
+        for (int64_t item = 0; item < total_items; ++item) {
+          mbar_wait(&s.full[stage], phase);
+          fence_proxy_async();
+          mbar_arrive_remote(mapa_u32(&s.full[stage], 0));
+          if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq);
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t tile = 0; tile < my_tiles; ++tile) {
         const int buf = (int)(tile & 1);
-        mbar_wait(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
+        if (PAIR) mbar_wait_cluster(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
+        else mbar_wait(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * t.buf_cols);
         for (int ks = 0; ks < t.n_ks; ++ks) {
-          mbar_wait(&s.full[stage], phase);
+          if (PAIR) mbar_wait_cluster(&s.full[stage], phase);
+          else mbar_wait(&s.full[stage], phase);
           fence_proxy_async();  // generic-proxy smem stores of the loaders -> async proxy (tensor core) reads
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.stage_base + (size_t)stage * sbytes);
@@ -328,12 +363,17 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
 #pragma unroll
           for (int k = 0; k < kSliceK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the swizzled row: +2 in the >>4 encoding
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_f16_2cta(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&s.empty[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs for PAIR) once these MMAs have read it
+          if (PAIR) umma_commit_2cta(&s.empty[stage]);
+          else umma_commit(&s.empty[stage]);
           if (++stage == t.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&s.tmem_full[buf]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs for PAIR)
+        if (PAIR) umma_commit_2cta(&s.tmem_full[buf]);
+        else umma_commit(&s.tmem_full[buf]);
       }
     }
   } else {
@@ -342,11 +382,12 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     bool flushed_once = false;
     for (int64_t tile = 0; tile < my_tiles; ++tile) {
       const int buf = (int)(tile & 1);
-      const int64_t ord = first + tile * stride;
-      const int64_t blk = mode_block_index(a, ord);
+      const int64_t ord = ord_of(tile);
+      const bool has_block = ord < a.n_mode_blocks;
+      const int64_t blk = has_block ? mode_block_index(a, ord) : 0;
       const int r_in = q * 32 + lane;
       const int64_t row = blk * kTileM + r_in;
-      bool valid = row < a.n_rows;
+      bool valid = has_block && row < a.n_rows;
       if (valid && a.row_allowed != nullptr) valid = a.row_allowed[row] != 0;
       const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
       const float lane_scale = (METRIC == RL_METRIC_COSINE && cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
@@ -363,7 +404,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
               float key = __uint_as_float(v[j]);
               if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
               else key *= lane_scale;
-              a.dump[(size_t)col * a.n_sample_rows + ord * kTileM + r_in] = valid ? key : kNegInf;
+              if (has_block) a.dump[(size_t)col * a.n_sample_rows + ord * kTileM + r_in] = valid ? key : kNegInf;
             }
           }
         } else {
@@ -415,7 +456,10 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[buf]);  // TMEM buffer is free for tile + 2
+      if (lane == 0) {  // TMEM buffer is free for tile + 2 (the leader CTA's barrier counts both epilogues)
+        if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(&s.tmem_empty[buf], 0));
+        else mbar_arrive(&s.tmem_empty[buf]);
+      }
       if (!a.dump_mode) {
         // Staged hits are flushed when enough have accumulated (or after the last tile): one global
         // atomic per query that was hit since the previous flush, plus the staged histogram.  The two
@@ -487,9 +531,11 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's smem / TMEM stay alive until the leader's last MMA has retired
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)t.tmem_cols);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, (uint32_t)t.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)t.tmem_cols);
   }
 }
 
@@ -583,24 +629,48 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     int cols = 32;
     while (cols < 2 * t.buf_cols) cols *= 2;
     t.tmem_cols = cols;
+    // cta_group::2 (SM pair) variant: validated bit-identical, but measured SLOWER than one CTA per SM on
+    // B200 (15.1 ms vs 12.6 ms on the 61 GB shard, same box: the peer->leader barrier relay and the
+    // coupling of two SMs cost more than the halved query stream saves), so it is opt-in: RL_TC_PAIR=1.
+    static const int pair_env = []() { const char* e = getenv("RL_TC_PAIR"); return e ? atoi(e) : 0; }();
+    const bool pair = pair_env == 1 && t.nq % 32 == 0 && t.nq >= 64 && a_in.n_mode_blocks >= 2 && sm_count >= 2;
     const uint32_t avail = kSmemBudget - 1024 - tail_bytes();
-    int stages = (int)(avail / stage_bytes(t.nq));
+    int stages = (int)(avail / stage_bytes(pair ? t.nq / 2 : t.nq));
     if (stages > kMaxStages) stages = kMaxStages;
     RL_REQUIRE(stages >= 2, RL_EUNSUPPORTED, "tcgen05 scan: not enough shared memory for 2 stages");
     t.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes(t.nq) + tail_bytes() + 1024;
+    const size_t smem = (size_t)stages * stage_bytes(pair ? t.nq / 2 : t.nq) + tail_bytes() + 1024;
     RL_REQUIRE(p->row_stats != nullptr, RL_EINVAL, "tcgen05 scan needs row_stats");
-    const int grid = (int)(a_in.n_mode_blocks < sm_count ? a_in.n_mode_blocks : sm_count);
-    auto launch = [&](auto kernel) -> int {
+    auto launch = [&](auto kernel, bool is_pair) -> int {
       RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kernel<<<grid, kThreads, smem, stream>>>(t);
-      RL_CUDA_CHECK(cudaGetLastError());
+      cudaLaunchConfig_t cfg{};
+      cudaLaunchAttribute attr[1];
+      if (is_pair) {
+        const int64_t n_pairs = (a_in.n_mode_blocks + 1) / 2;
+        const int clusters = (int)(n_pairs < sm_count / 2 ? n_pairs : sm_count / 2);
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+      } else {
+        cfg.gridDim = dim3((unsigned)(a_in.n_mode_blocks < sm_count ? a_in.n_mode_blocks : sm_count));
+      }
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      RL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, t));
       return RL_OK;
     };
     int rc;
-    if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE>);
-    else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT>);
-    else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2>);
+    if (pair) {
+      if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE, true>, true);
+      else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT, true>, true);
+      else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2, true>, true);
+    } else {
+      if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE, false>, false);
+      else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT, false>, false);
+      else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2, false>, false);
+    }
     if (rc != RL_OK) return rc;
   }
   return RL_OK;
