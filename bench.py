@@ -46,6 +46,8 @@ WORKLOADS = {
     "c2": dict(chunks=100_000, vecs=8, dim=384, batch=256, k=20,
                desc="BASELINE configs[1]: 100k chunks x 8 vecs x 384-d fp32, batch 256, top-20"),
     "tiny": dict(chunks=20_000, vecs=8, dim=128, batch=64, k=10, desc="debug"),
+    "c5": dict(chunks=0, vecs=0, dim=384, batch=1024, k=100,
+               desc="BASELINE configs[4]: cross-encoder rerank, MiniLM-L12-H384, 1024 queries x 100 candidates (seeded weights)"),
 }
 
 
@@ -233,9 +235,77 @@ def make_batch_queries(E, w: dict, seed: int):  # noqa: ANN001, ANN201
     return noise, rows
 
 
+def run_rerank(args: argparse.Namespace, w: dict) -> None:
+    """configs[4]: data-parallel over queries, one process per GPU, scores all-gathered at the end."""
+    import torch
+    import torch.distributed as dist
+
+    from oracle import rerank as orr        # seeded weights + the CPU arm only
+    from raglite_b200._xenc import CrossEncoderEngine
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_q, n_c = w["batch"], w["k"]
+    rng = np.random.default_rng(0)
+    lens = np.clip(rng.normal(200, 60, size=n_q * n_c).astype(int), 32, 512)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        model = orr.seeded_model(seed=0)
+        n = 64
+        ids = [rng.integers(1000, 30000, size=L).astype(np.int32) for L in lens[:n]]
+        types = [np.r_[np.zeros(12, np.int32), np.ones(L - 12, np.int32)] for L in lens[:n]]
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        t0 = time.perf_counter(); orr.hf_logits(model, ids, types); dt = time.perf_counter() - t0
+        v = n / dt
+        print(json.dumps({"impl": "reference", "metric": "cross-encoder pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": w["desc"]},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                                           "sample": f"{n} pairs, transformers BertForSequenceClassification fp32"},
+                          "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = CrossEncoderEngine.from_hf(orr.seeded_model(seed=0))
+    mine = np.arange(rank, n_q, world)                       # this rank's queries
+    sel = np.concatenate([np.arange(q * n_c, (q + 1) * n_c) for q in mine])
+    ids = [rng.integers(1000, 30000, size=L).astype(np.int32) for L in lens[sel]]
+    types = [np.r_[np.zeros(12, np.int32), np.ones(L - 12, np.int32)] for L in lens[sel]]
+    eng.score_tokens(ids[:256], types[:256])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    _, scores = eng.score_tokens(ids, types)                  # host ids in -> host scores out
+    order = np.argsort(-scores.reshape(len(mine), n_c), axis=1, kind="stable")   # rerank_chunks' reorder
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total = n_q * n_c
+        v = total / float(dt.item())
+        tok = int(lens.sum())
+        line = {"metric": "cross-encoder pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": float(dt.item()) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16", "data": "synthetic (seeded weights, random token pairs, mean 200 tokens)",
+                "config": {"workload": w["desc"], "pairs": total, "tokens": tok, "parallelism": f"dp{world} over queries"},
+                "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(tok * 12 // world), "d2h_bytes_per_step": int(total * 8 // world)},
+                "gpu_launches": int(86 * np.ceil(tok / world / eng.max_tokens_per_call)), "reordered": int(order.shape[0])}
+        sys.stdout.flush(); os.dup2(saved, 1); print(json.dumps(line), flush=True); os.dup2(2, 1)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main() -> None:  # noqa: PLR0915
     args = parse_args()
     w = resolve(args)
+    if w["name"] == "c5":
+        run_rerank(args, w)
+        return
     if args.impl == "reference":
         run_reference(args, w)
         return

@@ -8,6 +8,7 @@ Drop-in surface (reference ``raglite/__init__.py`` names for this path): ``RAGLi
 from ._config import RAGLiteConfig
 from ._embed import embed_strings, register_token_embedder
 from ._index import Chunk, CorpusIndex, get_index, merge_hits, register_index, unregister_index
+from ._query_adapter import reciprocal_rank_fusion, update_query_adapter
 from ._search import rerank_chunks, retrieve_chunks, vector_search, vector_search_batch
 
 __all__ = [
@@ -18,10 +19,12 @@ __all__ = [
     "get_index",
     "merge_hits",
     "register_index",
+    "reciprocal_rank_fusion",
     "register_token_embedder",
     "rerank_chunks",
     "retrieve_chunks",
     "unregister_index",
+    "update_query_adapter",
     "vector_search",
     "vector_search_batch",
 ]

@@ -1,0 +1,117 @@
+"""Query adapter: apply (hot path) and fit (the caller that produces ``A``).
+
+Apply -- ``(A @ q).astype(q.dtype)`` (reference ``_search.py:58-62``) -- runs in ``rl_adapter_apply``
+via ``CorpusIndex.apply_adapter``.  The fit follows ``raglite/_query_adapter.py:141-219``: for every
+eval, embed the question, retrieve the top chunks *without* the adapter, take each chunk's best
+vector for the query (MaxSim ``argmax(E_c @ q)``, ``:172-183``) as a positive or negative, solve the
+bounded least squares for the target ``t`` (``:21-38``), then ``M = T^T Q / n`` (+ null-space
+completion) and the orthogonal Procrustes / Frobenius-scaled solution (``:193-205``).  Retrieval and
+the per-chunk MaxSim run on the GPU index; the small dense algebra (NNLS, SVD) stays in SciPy/NumPy
+float64 exactly as in the reference.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Sequence
+from dataclasses import replace
+from typing import Any
+
+import numpy as np
+import torch
+from scipy.optimize import lsq_linear
+
+from ._config import RAGLiteConfig
+from ._index import CorpusIndex, get_index
+from ._search import vector_search_batch
+
+
+def _optimize_query_target(q: np.ndarray, P: np.ndarray, N: np.ndarray, *, alpha: float = 0.05) -> np.ndarray:
+    """Dual of ``min ||t - q||`` s.t. every positive beats every negative by a margin (``:21-38``)."""
+    dtype = q.dtype
+    q64, P64, N64 = q.astype(np.float64), P.astype(np.float64), N.astype(np.float64)
+    D = (P64[:, None, :] - (1.0 + alpha) * N64[None, :, :]).reshape(-1, P64.shape[1])
+    mu = lsq_linear(D.T, -q64, bounds=(0.0, np.inf), tol=np.finfo(np.float64).eps).x
+    return (q64 + D.T @ mu).astype(dtype)
+
+
+def _best_vectors(index: CorpusIndex, chunks: Sequence[int], q: np.ndarray) -> np.ndarray:
+    """Row ``argmax(E_c @ q)`` of every chunk in ``chunks`` (one gather + one matvec on the device)."""
+    off = index.chunk_off
+    rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in chunks])
+    seg = np.cumsum([0] + [int(off[c + 1] - off[c]) for c in chunks])
+    E = index.E[torch.from_numpy(rows).to(index.device)]
+    s = (E @ torch.from_numpy(q.astype(np.float32)).to(index.device)).cpu().numpy()
+    best = [rows[seg[i] + int(np.argmax(s[seg[i]:seg[i + 1]]))] for i in range(len(chunks))]
+    return index.E[torch.from_numpy(np.asarray(best)).to(index.device)].cpu().numpy()
+
+
+def update_query_adapter(  # noqa: PLR0913
+    evals: Sequence[tuple[np.ndarray, Sequence[int]]],
+    *,
+    max_evals: int = 4096,
+    optimize_top_k: int = 40,
+    optimize_gap: float = 0.05,
+    config: RAGLiteConfig | None = None,
+    index: Any | None = None,
+) -> np.ndarray:
+    """Compute the optimal query adapter and attach it to the index.
+
+    ``evals`` are ``(question_embedding, relevant_chunk_indices)`` pairs -- what the reference reads from
+    its ``Eval`` table and ``embed_strings`` (``_query_adapter.py:151-160``).
+    """
+    config = config or RAGLiteConfig()
+    index = index if index is not None else get_index(config)
+    local: CorpusIndex = getattr(index, "local", index)
+    if local is None or local.n_rows == 0:
+        raise ValueError("First insert documents (the index is empty).")
+    if len(evals) == 0:
+        raise ValueError("First generate evals.")
+    metric = config.vector_search_distance_metric
+    if metric not in ("cosine", "dot"):
+        raise ValueError(f"Unsupported metric: {metric}")
+    cfg_no_adapter = replace(config, vector_search_query_adapter=False)
+    evals = list(evals)[:max_evals]
+    Qm = np.stack([np.ravel(q) for q, _ in evals])
+    ids, _, counts = vector_search_batch(Qm, num_results=optimize_top_k, config=cfg_no_adapter, index=index)
+    Qs, Ts = [], []
+    for e, (q, relevant) in enumerate(evals):
+        retrieved = [int(c) for c in ids[e, : counts[e]]]
+        is_rel = np.array([c in set(int(r) for r in relevant) for c in retrieved], dtype=bool)
+        if not is_rel.any() or is_rel.all():
+            continue
+        q = np.ravel(q)
+        best = _best_vectors(local, retrieved, q)
+        t = _optimize_query_target(q, best[is_rel], best[~is_rel], alpha=optimize_gap)
+        Qs.append(q.astype(np.float64))
+        Ts.append(t.astype(np.float64))
+    if not Qs:
+        raise ValueError("No eval had both relevant and irrelevant chunks among the retrieved ones.")
+    Q, T = np.vstack(Qs), np.vstack(Ts)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    if metric == "cosine":
+        T /= np.linalg.norm(T, axis=1, keepdims=True)
+    n, d = Q.shape
+    M = (1 / n) * T.T @ Q
+    if n < d or np.linalg.matrix_rank(Q) < d:
+        M += np.eye(d) - Q.T @ np.linalg.pinv(Q @ Q.T) @ Q
+    if metric == "dot":
+        A_star = M / np.linalg.norm(M, ord="fro") * np.sqrt(d)
+    else:
+        U, _, VT = np.linalg.svd(M, full_matrices=False)
+        A_star = U @ VT
+    local.set_query_adapter(A_star)
+    return A_star
+
+
+def reciprocal_rank_fusion(rankings: Sequence[Sequence[str]], *, k: int = 60, weights: Sequence[float] | None = None
+                           ) -> tuple[list[str], list[float]]:
+    """Reciprocal Rank Fusion (``_search.py:233-254``): ``score(c) = sum_r w_r / (k + rank_r(c))``."""
+    weights = [1.0] * len(rankings) if weights is None else list(weights)
+    if len(weights) != len(rankings):
+        raise ValueError("The number of weights must match the number of rankings.")
+    score: dict[str, float] = {}
+    for ranking, w in zip(rankings, weights, strict=True):
+        for pos, cid in enumerate(ranking):
+            score[cid] = score.get(cid, 0.0) + w / (k + pos)
+    order = sorted(score.items(), key=lambda kv: kv[1], reverse=True)
+    return [c for c, _ in order], [s for _, s in order]

@@ -269,3 +269,38 @@ def test_two_shards_merge_equals_single_index(rl):
                 check_sql_semantics(E, off, Q[i], chunk[i, :count[i]], sim[i, :count[i]], k=20)
             else:
                 check_exact_maxsim(E, off, Q[i], chunk[i, :count[i]], sim[i, :count[i]], k=20)
+
+
+def test_update_query_adapter_matches_oracle_fit(rl):
+    """Adapter fit: GPU retrieval + MaxSim picks, then the reference's float64 algebra."""
+    from oracle import adapter as oad
+
+    E, off = make_corpus(400, (1, 6), 48, seed=61)
+    rng = np.random.default_rng(62)
+    cfg = rl.RAGLiteConfig(db_url="mem://fit", reranker=None)
+    idx = rl.CorpusIndex(E, off)
+    rl.register_index(cfg, idx)
+    evals = []
+    for _ in range(12):
+        c = int(rng.integers(0, len(off) - 1))
+        q = E[off[c]] + 0.4 * rng.standard_normal(48).astype(np.float32)
+        evals.append((q / np.linalg.norm(q), [c, int(rng.integers(0, len(off) - 1))]))
+    A = rl.update_query_adapter(evals, optimize_top_k=10, config=cfg)
+    assert A.shape == (48, 48) and np.isfinite(A).all()                  # tests/test_query_adapter.py:24-27
+    assert np.allclose(A @ A.T, np.eye(48), atol=1e-9)                    # orthogonal Procrustes
+    assert np.array_equal(idx.query_adapter, A)
+    # oracle: same triplets through the NumPy restatement
+    Qs, Ts = [], []
+    for q, rel in evals:
+        ids, _ = ovs.maxsim_topk_exact(E, off, q, 10)
+        sql_ids, _, _ = ovs.vector_search_sql(E, off, q, num_results=10, f64=True)
+        is_rel = np.array([c in rel for c in sql_ids])
+        if not is_rel.any() or is_rel.all():
+            continue
+        best = np.stack([E[off[c]:off[c + 1]][oad.maxsim_row(E[off[c]:off[c + 1]], q)] for c in sql_ids])
+        Ts.append(oad.optimize_query_target(q, best[is_rel], best[~is_rel], alpha=0.05)); Qs.append(q)
+    want = oad.fit_query_adapter(np.vstack(Qs), np.vstack(Ts), "cosine")
+    assert np.allclose(A, want, atol=1e-8)
+    _, s_on = rl.vector_search(evals[0][0], num_results=5, config=cfg)
+    _, s_off = rl.vector_search(evals[0][0], num_results=5, config=rl.RAGLiteConfig(db_url="mem://fit", reranker=None, vector_search_query_adapter=False))
+    assert s_on != s_off
