@@ -107,7 +107,7 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   if (cap <= 0) {
     // ~3-4x sel_final candidates survive the refined thresholds, plus the burst before the first
     // refresh; the static bound (4 * sel_final * S) only applies to the fp32 scan, which does not refine.
-    cap = algo == RL_ALGO_TCGEN05 ? 32 * sel_final + 8192 : 4 * sel_final * S + 1024;
+    cap = algo == RL_ALGO_TCGEN05 ? 64 * sel_final + 16384 : 4 * sel_final * S + 1024;
     if (cap > p->n_rows + 1024) cap = p->n_rows + 1024;
   }
   if (cap < 256) cap = 256;
