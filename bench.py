@@ -66,6 +66,8 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--adapter", default="auto", choices=["auto", "on", "off"], help="query adapter apply (on for c3)")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--sample-stride", type=int, default=0, help="override the sampling stride (0 = library heuristic)")
+    ap.add_argument("--storage", default="fp32", choices=["fp32", "fp16"],
+                    help="fp16: corpus rounded to float16 and stored as such (lossless layout for RAGLite data)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0)
@@ -205,14 +207,15 @@ def run_reference(args: argparse.Namespace, w: dict) -> None:
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------------
-def build_shard(w: dict, rank: int, device):  # noqa: ANN001, ANN201
-    """Synthetic unit-norm fp32 corpus shard generated on the device (seeded per rank)."""
+def build_shard(w: dict, rank: int, device, storage: str = "fp32"):  # noqa: ANN001, ANN201
+    """Synthetic unit-norm corpus shard generated on the device (seeded per rank); float32, or rounded
+    to float16 (what RAGLite stores, _embed.py:140) for the fp16 layout."""
     import torch
 
     n_rows = w["chunks"] * w["vecs"]
     g = torch.Generator(device=device)
     g.manual_seed(1234 + rank)
-    E = torch.empty((n_rows, w["dim"]), dtype=torch.float32, device=device)
+    E = torch.empty((n_rows, w["dim"]), dtype=torch.float16 if storage == "fp16" else torch.float32, device=device)
     step = 1 << 20
     for r0 in range(0, n_rows, step):
         r1 = min(n_rows, r0 + step)
@@ -240,8 +243,7 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
     import torch
     import torch.distributed as dist
 
-    from oracle import rerank as orr        # seeded weights + the CPU arm only
-    from raglite_b200._xenc import CrossEncoderEngine
+    from raglite_b200._xenc import CrossEncoderEngine, random_minilm_state_dict
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,6 +253,7 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
     if args.impl == "reference":
         if rank != 0:
             return
+        from oracle import rerank as orr     # the CPU arm: float32 transformers forward
         model = orr.seeded_model(seed=0)
         n = 64
         ids = [rng.integers(1000, 30000, size=L).astype(np.int32) for L in lens[:n]]
@@ -269,7 +272,7 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = CrossEncoderEngine.from_hf(orr.seeded_model(seed=0))
+    eng = CrossEncoderEngine(random_minilm_state_dict(0), n_layers=12, hidden=384, n_heads=12, ffn=1536, max_pos=512)
     mine = np.arange(rank, n_q, world)                       # this rank's queries
     sel = np.concatenate([np.arange(q * n_c, (q + 1) * n_c) for q in mine])
     ids = [rng.integers(1000, 30000, size=L).astype(np.int32) for L in lens[sel]]
@@ -331,15 +334,16 @@ def main() -> None:  # noqa: PLR0915
         dist.init_process_group("nccl", device_id=device)
 
     B, k, num_hits, d = w["batch"], w["k"], w["num_hits"], w["dim"]
-    E = build_shard(w, rank, device)
+    E = build_shard(w, rank, device, args.storage)
     chunk_off = np.arange(0, E.shape[0] + 1, w["vecs"], dtype=np.int64)
-    local = rl.CorpusIndex(E, chunk_off, chunk_base=rank * w["chunks"], device=device)
+    local = rl.CorpusIndex(E, chunk_off, chunk_base=rank * w["chunks"], device=device, storage=args.storage)
+    esize = 2 if args.storage == "fp16" else 4
     del E
     index = ShardedIndex(local, group=dist.group.WORLD if world > 1 else None)
 
     # Queries: built from rank 0's rows so that every rank sees the same batch.
     noise, rows = make_batch_queries(local.E, w, seed=99)
-    base = local.E[rows.to(device)].clone()
+    base = local.E[rows.to(device)].float().clone()
     if world > 1:
         dist.broadcast(base, src=0)
     Qd = base + 0.3 * noise.to(device)
@@ -420,7 +424,7 @@ def main() -> None:  # noqa: PLR0915
     S = max(1, stats["sample_stride"])
     n_blocks = (n_rows + 127) // 128
     main_rows = min(n_rows, (n_blocks - (n_blocks + S - 1) // S) * 128)
-    alg_bytes = main_rows * d * 4 + main_rows * 4 + B * d * 4        # corpus rows once + inv_norm + queries
+    alg_bytes = main_rows * d * esize + main_rows * 4 + B * d * 4    # corpus rows once + inv_norm + queries
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -430,7 +434,8 @@ def main() -> None:  # noqa: PLR0915
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(w["name"])
-        if tr and w["chunks"] == WORKLOADS[w["name"]]["chunks"] and B == WORKLOADS[w["name"]]["batch"] and not args.exact_maxsim:
+        if (tr and w["chunks"] == WORKLOADS[w["name"]]["chunks"] and B == WORKLOADS[w["name"]]["batch"]
+                and not args.exact_maxsim and args.storage == "fp32"):
             traffic = tr["traffic_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
@@ -479,7 +484,7 @@ def main() -> None:  # noqa: PLR0915
             short = []
             stepr = 1 << 21
             for r0 in range(0, n_rows, stepr):
-                s = (local.E[r0:r0 + stepr] @ Qc[b]) * local.inv_norm[r0:r0 + stepr]
+                s = (local.E[r0:r0 + stepr].float() @ Qc[b]) * local.inv_norm[r0:r0 + stepr]
                 short.append(torch.topk(s, min(take, s.numel())).indices + r0)
             rows_c = torch.cat(short)
             e64 = local.E[rows_c].double()
@@ -506,13 +511,14 @@ def main() -> None:  # noqa: PLR0915
             "metric": "queries/sec multi-vector MaxSim over 10M chunks", "value": qps_raw * norm,
             "unit": "queries/s (10M-chunk equivalent)", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.storage == "fp32" else "f16", "data": "synthetic",
             "config": {"workload": w["desc"], "chunks_per_gpu": w["chunks"], "vecs_per_chunk": w["vecs"], "dim": d,
                        "batch": B, "k": k, "num_hits": num_hits, "metric": "cosine", "query_adapter": use_adapter,
+                       "corpus_storage": args.storage,
                        "semantics": "exact MaxSim" if args.exact_maxsim else "reference SQL (top-num_hits vectors -> group max -> top-k)",
                        "chunks_scanned": total_chunks, "normalisation": "value = batch / t_step * chunks_scanned / 10M",
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of per-shard hits" if world > 1 else "single GPU shard",
-                       "l2": "corpus shard (%.1f GB) >> L2, no flush needed" % (n_rows * d * 4 / 1e9)},
+                       "l2": "corpus shard (%.1f GB) >> L2, no flush needed" % (n_rows * d * esize / 1e9)},
             "queries_per_sec_raw": qps_raw,
             "e2e": {"value": e2e_value, "unit": "queries/s (10M-chunk equivalent)", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4),

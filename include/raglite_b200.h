@@ -65,6 +65,9 @@ int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes
  * chunk_embedding table (_database.py:403-430). */
 int rl_row_stats(const float* E, int64_t n_rows, int d, int64_t ld, float* inv_norm, float* sq_norm,
                  float* stats, void* stream);
+/* Same for an embedding matrix stored as float16 (rl_scan_params.e_dtype == 1). */
+int rl_row_stats_f16(const void* E, int64_t n_rows, int d, int64_t ld, float* inv_norm, float* sq_norm,
+                     float* stats, void* stream);
 
 /* row_chunk[j] = c for chunk_off[c] <= j < chunk_off[c+1]  (CSR -> per-row owner; the
  * chunk_embedding.chunk_id column, _database.py:421). */
@@ -113,6 +116,8 @@ typedef struct rl_scan_params {
   uint32_t flags;
   int32_t sample_stride; /* 0 = auto */
   int32_t cand_cap;      /* 0 = auto */
+  int32_t e_dtype;       /* storage of E: 0 = float32, 1 = float16 (E then points to IEEE binary16; needs
+                            RL_ALGO_TCGEN05, d % 8 == 0 and rows that need no per-row scaling) */
 } rl_scan_params;
 
 size_t rl_maxsim_workspace_bytes(const rl_scan_params* p);

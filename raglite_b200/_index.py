@@ -93,6 +93,7 @@ class CorpusIndex:
         chunks: Sequence[Chunk] | None = None,
         chunk_metadata: Sequence[dict[str, Any]] | None = None,
         device: torch.device | str | None = None,
+        storage: str = "fp32",
     ) -> None:
         if not torch.cuda.is_available():
             raise RuntimeError("raglite_b200 needs a CUDA device (there is no CPU fallback)")
@@ -101,8 +102,25 @@ class CorpusIndex:
         E = torch.as_tensor(embeddings)
         if E.ndim != 2:
             raise ValueError("embeddings must be [n_rows, d]")
-        self.E = E.to(device=self.device, dtype=torch.float32).contiguous()
+        if storage not in ("fp32", "fp16"):
+            raise ValueError("storage must be 'fp32' or 'fp16'")
+        self.storage = storage
+        if storage == "fp16":
+            # Lossless only: RAGLite's embeddings are fp16-rounded already (_embed.py:140) and DuckDB merely
+            # widens them to FLOAT[d]; anything else must stay float32.
+            Eh = E.to(device=self.device, dtype=torch.float16).contiguous()
+            if E.dtype != torch.float16:
+                step = 1 << 20
+                for r0 in range(0, int(E.shape[0]), step):
+                    blk = E[r0:r0 + step].to(self.device, dtype=torch.float32)
+                    if not torch.equal(Eh[r0:r0 + step].float(), blk):
+                        raise ValueError("storage='fp16' needs embeddings that are exactly representable in float16")
+            self.E = Eh
+        else:
+            self.E = E.to(device=self.device, dtype=torch.float32).contiguous()
         self.n_rows, self.d = int(self.E.shape[0]), int(self.E.shape[1])
+        if storage == "fp16" and self.d % 8:
+            raise ValueError("storage='fp16' needs d % 8 == 0")
         if chunk_offsets is None:
             v = 1 if vecs_per_chunk is None else int(vecs_per_chunk)
             if self.n_rows % v:
@@ -131,11 +149,40 @@ class CorpusIndex:
             self.stats = torch.zeros(4, dtype=torch.float32, device=self.device)
             self.row_chunk = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
             off_dev = torch.from_numpy(self.chunk_off).to(self.device)
-            check(self.lib.rl_row_stats(_ptr(self.E), self.n_rows, self.d, self.d, _ptr(self.inv_norm),
-                                        _ptr(self.sq_norm), _ptr(self.stats), _stream()), "rl_row_stats")
+            stats_fn = self.lib.rl_row_stats_f16 if storage == "fp16" else self.lib.rl_row_stats
+            check(stats_fn(_ptr(self.E), self.n_rows, self.d, self.d, _ptr(self.inv_norm),
+                           _ptr(self.sq_norm), _ptr(self.stats), _stream()), "rl_row_stats")
             check(self.lib.rl_chunk_row_map(_ptr(off_dev), self.n_chunks, _ptr(self.row_chunk), _stream()),
                   "rl_chunk_row_map")
             torch.cuda.current_stream().synchronize()
+            if storage == "fp16" and self.n_rows:
+                st = self.stats.cpu().numpy()
+                self._fp16_cosine_ok = bool(0.0 < st[2] <= 2.0 and st[1] <= 1024.0 and st[3] == 0.0)
+
+    @classmethod
+    def from_chunk_embedding_rows(cls, row_chunk_ids: Sequence[ChunkId], embeddings: torch.Tensor | np.ndarray,
+                                  **kw: Any) -> "CorpusIndex":
+        """Build the index from the rows of RAGLite's ``chunk_embedding`` table read in insertion order
+        (``SELECT chunk_id, embedding FROM chunk_embedding ORDER BY id``; ``_database.py:403-430``): a
+        chunk's vectors are contiguous (``_insert.py:247-251``), so consecutive equal ``chunk_id`` values
+        form one CSR segment.  A chunk id that re-appears after another chunk is a layout error."""
+        ids = list(row_chunk_ids)
+        E = torch.as_tensor(embeddings)
+        if len(ids) != int(E.shape[0]):
+            raise ValueError("one chunk_id per embedding row is required")
+        offsets, chunk_ids, seen = [0], [], set()
+        for i, cid in enumerate(ids):
+            if i == 0 or cid != ids[i - 1]:
+                if cid in seen:
+                    raise ValueError(f"chunk_id {cid!r} is not contiguous in the chunk_embedding rows")
+                seen.add(cid)
+                chunk_ids.append(cid)
+                if i:
+                    offsets.append(i)
+        offsets.append(len(ids))
+        if not ids:
+            offsets = [0]
+        return cls(E, np.asarray(offsets, dtype=np.int64), chunk_ids=chunk_ids, **kw)
 
     # ---- query adapter (IndexMetadata.get("default")["query_adapter"], _search.py:60) ------------
     def set_query_adapter(self, A: np.ndarray | None) -> None:
@@ -169,6 +216,9 @@ class CorpusIndex:
         p.Q, p.B = _ptr(Q), int(Q.shape[0])
         p.metric, p.k, p.num_hits, p.algo = RL_METRIC[metric], int(k), int(num_hits), RL_ALGO[algo]
         p.flags, p.sample_stride, p.cand_cap = flags, sample_stride, cand_cap
+        p.e_dtype = 1 if self.storage == "fp16" else 0
+        if self.storage == "fp16" and metric == "cosine" and not getattr(self, "_fp16_cosine_ok", True):
+            raise ValueError("storage='fp16' with the cosine metric needs rows with norm >= 0.5 (normalised embeddings)")
         return p
 
     def scan(  # noqa: PLR0913

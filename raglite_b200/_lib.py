@@ -21,7 +21,7 @@ RL_STATUS_TIE_OVERFLOW = 2
 RL_MAX_SURVIVORS = 4096
 
 EXPORTS = [
-    "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_chunk_row_map", "rl_adapter_apply",
+    "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
     "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_copy_dump", "rl_topk_merge",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
@@ -36,7 +36,7 @@ class ScanParams(C.Structure):
         ("d", C.c_int32), ("max_vecs_per_chunk", C.c_int32),
         ("Q", C.c_void_p),
         ("B", C.c_int32), ("metric", C.c_int32), ("k", C.c_int32), ("num_hits", C.c_int32), ("algo", C.c_int32),
-        ("flags", C.c_uint32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32),
+        ("flags", C.c_uint32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32), ("e_dtype", C.c_int32),
     ]
 
 
@@ -73,6 +73,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_last_error.restype = C.c_char_p
     lib.rl_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
     lib.rl_row_stats.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp]
+    lib.rl_row_stats_f16.argtypes = [vp, i64, i32, i64, vp, vp, vp, vp]
     lib.rl_chunk_row_map.argtypes = [vp, i64, vp, vp]
     lib.rl_adapter_apply.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.rl_maxsim_workspace_bytes.argtypes = [C.POINTER(ScanParams)]

@@ -39,10 +39,10 @@ def _best_vectors(index: CorpusIndex, chunks: Sequence[int], q: np.ndarray) -> n
     off = index.chunk_off
     rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in chunks])
     seg = np.cumsum([0] + [int(off[c + 1] - off[c]) for c in chunks])
-    E = index.E[torch.from_numpy(rows).to(index.device)]
+    E = index.E[torch.from_numpy(rows).to(index.device)].float()
     s = (E @ torch.from_numpy(q.astype(np.float32)).to(index.device)).cpu().numpy()
     best = [rows[seg[i] + int(np.argmax(s[seg[i]:seg[i + 1]]))] for i in range(len(chunks))]
-    return index.E[torch.from_numpy(np.asarray(best)).to(index.device)].cpu().numpy()
+    return index.E[torch.from_numpy(np.asarray(best)).to(index.device)].float().cpu().numpy()
 
 
 def update_query_adapter(  # noqa: PLR0913

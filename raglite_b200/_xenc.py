@@ -25,6 +25,35 @@ def _stream() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 
 
+def random_minilm_state_dict(seed: int = 0, *, n_layers: int = 12, hidden: int = 384, ffn: int = 1536,
+                             vocab: int = 30522, max_pos: int = 512) -> dict[str, torch.Tensor]:
+    """Seeded random weights with the HF ``BertForSequenceClassification`` names/shapes of
+    ms-marco-MiniLM-L-12-v2 (real weights cannot be downloaded offline); for benchmarks and smoke tests."""
+    g = torch.Generator().manual_seed(seed)
+
+    def w(*shape: int) -> torch.Tensor:
+        return torch.randn(shape, generator=g) * 0.02
+
+    sd = {
+        "bert.embeddings.word_embeddings.weight": w(vocab, hidden),
+        "bert.embeddings.position_embeddings.weight": w(max_pos, hidden),
+        "bert.embeddings.token_type_embeddings.weight": w(2, hidden),
+        "bert.embeddings.LayerNorm.weight": torch.ones(hidden), "bert.embeddings.LayerNorm.bias": torch.zeros(hidden),
+        "bert.pooler.dense.weight": w(hidden, hidden), "bert.pooler.dense.bias": torch.zeros(hidden),
+        "classifier.weight": w(1, hidden) * 8.0, "classifier.bias": torch.zeros(1),
+    }
+    for l in range(n_layers):
+        p = f"bert.encoder.layer.{l}."
+        for n in ("query", "key", "value"):
+            sd[p + f"attention.self.{n}.weight"], sd[p + f"attention.self.{n}.bias"] = w(hidden, hidden), torch.zeros(hidden)
+        sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"] = w(hidden, hidden), torch.zeros(hidden)
+        sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"] = torch.ones(hidden), torch.zeros(hidden)
+        sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"] = w(ffn, hidden), torch.zeros(ffn)
+        sd[p + "output.dense.weight"], sd[p + "output.dense.bias"] = w(hidden, ffn), torch.zeros(hidden)
+        sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"] = torch.ones(hidden), torch.zeros(hidden)
+    return sd
+
+
 class CrossEncoderEngine:
     """Device-resident packed weights + tokenizer + batching."""
 

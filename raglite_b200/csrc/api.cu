@@ -66,6 +66,7 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   RL_REQUIRE(p->num_hits >= 0, RL_EINVAL, "num_hits must be >= 0");
   RL_REQUIRE(p->metric >= RL_METRIC_COSINE && p->metric <= RL_METRIC_L2, RL_EINVAL, "unknown metric %d", p->metric);
   RL_REQUIRE(p->max_vecs_per_chunk >= 1, RL_EINVAL, "max_vecs_per_chunk must be >= 1");
+  RL_REQUIRE(p->e_dtype == 0 || p->e_dtype == 1, RL_EINVAL, "e_dtype must be 0 (float32) or 1 (float16)");
   memset(L, 0, sizeof(*L));
   L->mode_sql = p->num_hits > 0;
   L->H = L->mode_sql ? p->num_hits : p->k;
@@ -80,6 +81,8 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   const bool tc_ok = tcgen05_supported(p);
   if (algo == RL_ALGO_AUTO) algo = tc_ok ? RL_ALGO_TCGEN05 : RL_ALGO_FP32;
   RL_REQUIRE(algo == RL_ALGO_FP32 || algo == RL_ALGO_TCGEN05, RL_EINVAL, "unknown algo %d", p->algo);
+  RL_REQUIRE(p->e_dtype == 0 || algo == RL_ALGO_TCGEN05, RL_EUNSUPPORTED,
+             "float16 storage needs the tcgen05 scan (d %% 8 == 0, ld %% 8 == 0, 16-byte aligned E)");
   RL_REQUIRE(algo != RL_ALGO_TCGEN05 || tc_ok, RL_EUNSUPPORTED,
              "RL_ALGO_TCGEN05 needs d %% 4 == 0, ld %% 4 == 0, 16-byte aligned E and a supported metric");
   L->algo = algo;
@@ -268,7 +271,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   f.n_surv = n_surv; f.header = hdr; f.ld = p->ld; f.chunk_base = p->chunk_base; f.n_sample_rows = L.n_sample_rows;
   f.d = p->d; f.metric = p->metric; f.cap = L.cap; f.mode_sql = L.mode_sql;
   f.sel_k = L.mode_sql ? p->num_hits : (p->k - 1) * p->max_vecs_per_chunk + 1;
-  f.H = L.H; f.launches = launches + 1; f.S = L.S; f.algo = L.algo;
+  f.H = L.H; f.launches = launches + 1; f.S = L.S; f.algo = L.algo; f.e_f16 = p->e_dtype;
   rc = launch_finalize(f, p->B, stream);
   mark(5);
   return rc;

@@ -68,6 +68,48 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict_
   }
 }
 
+// Same statistics for a float16 matrix (8 halves per 16-byte load).
+__global__ void __launch_bounds__(256) row_stats_f16_kernel(const __half* __restrict__ E, int64_t n_rows, int d,
+                                                            int64_t ld, float* __restrict__ inv_norm,
+                                                            float* __restrict__ sq_norm, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float max_norm = 0.f, max_abs = 0.f, max_inv = 0.f;
+  bool zero_row = false;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const __half* row = E + r * ld;
+    double s = 0.0;
+    float ma = 0.f;
+    for (int c = lane * 8; c < d; c += 256) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        s += (double)f.x * f.x + (double)f.y * f.y;
+        ma = fmaxf(ma, fmaxf(fabsf(f.x), fabsf(f.y)));
+      }
+    }
+    s = warp_sum(s);
+    ma = warp_max(ma);
+    if (lane == 0) {
+      inv_norm[r] = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
+      sq_norm[r] = (float)s;
+      max_norm = fmaxf(max_norm, (float)sqrt(s));
+      max_abs = fmaxf(max_abs, ma);
+      if (s > 0.0) max_inv = fmaxf(max_inv, (float)(1.0 / sqrt(s)));
+      else zero_row = true;
+    }
+  }
+  if (lane == 0 && stats != nullptr) {
+    atomicMax(reinterpret_cast<int*>(stats + 0), __float_as_int(max_norm));
+    atomicMax(reinterpret_cast<int*>(stats + 1), __float_as_int(max_abs));
+    atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(max_inv));
+    if (zero_row) atomicMax(reinterpret_cast<int*>(stats + 3), __float_as_int(1.f));
+  }
+}
+
 __global__ void chunk_row_map_kernel(const int64_t* __restrict__ chunk_off, int64_t n_chunks,
                                      int32_t* __restrict__ row_chunk) {
   for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks;
@@ -158,6 +200,21 @@ extern "C" int rl_row_stats(const float* E, int64_t n_rows, int d, int64_t ld, f
   const int64_t blocks = (n_rows + 7) / 8;
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
   row_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(E, n_rows, d, ld, inv_norm, sq_norm, stats);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+extern "C" int rl_row_stats_f16(const void* E, int64_t n_rows, int d, int64_t ld, float* inv_norm, float* sq_norm,
+                                float* stats, void* stream) {
+  RL_REQUIRE(n_rows >= 0 && d > 0 && ld >= d, RL_EINVAL, "rl_row_stats_f16: bad shape");
+  RL_REQUIRE(d % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(E) & 15) == 0, RL_EUNSUPPORTED,
+             "rl_row_stats_f16: d and ld must be multiples of 8 and E 16-byte aligned");
+  if (n_rows == 0) return RL_OK;
+  RL_REQUIRE(E && inv_norm && sq_norm, RL_EINVAL, "rl_row_stats_f16: null pointer");
+  const int64_t blocks = (n_rows + 7) / 8;
+  const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  row_stats_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(E), n_rows, d, ld, inv_norm,
+                                                               sq_norm, stats);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }

@@ -14,11 +14,14 @@
 //     accumulator buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1,
 //   * 4 epilogue warps read the accumulators with tcgen05.ld (lane = corpus row, column = query),
 //     turn them into keys and either dump them (sample tiles) or compare them with the per-query
-//     threshold and append the few survivors to the candidate lists.
+//     threshold; the few survivors are staged in shared memory together with a histogram of their
+//     keys, flushed in bulk (one global atomic per touched query / bin), and the global histogram is
+//     read back to tighten the thresholds while the scan is running (online refinement).
 // All hand-offs are mbarrier based (full/empty per smem stage, full/empty per TMEM buffer).
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "scan_tcgen05.cuh"
 #include "tcgen05_ptx.cuh"
@@ -90,7 +93,9 @@ __host__ __device__ inline uint32_t tail_bytes() {
 
 // PAIR: two CTAs of a cluster (an SM pair) issue one cta_group::2 MMA (M = 256: 128 rows per CTA) and
 // each holds only half of the queries in shared memory, which halves the L2 -> SM query stream.
-template <int METRIC, bool PAIR>
+// EF16: the corpus is stored as fp16 (lossless for RAGLite data, whose embeddings are fp16-rounded,
+// reference _embed.py:140): rows are copied into the swizzled tile without conversion, half the HBM bytes.
+template <int METRIC, bool PAIR, bool EF16>
 __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   const ScanArgs& a = t.a;
@@ -160,10 +165,110 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   const uint32_t tmem_base = *s.tmem_ptr;
   // Cosine on a corpus whose rows all have norm >= 0.5 and moderate magnitudes (the normal case:
   // embeddings are stored normalised): rows go to fp16 unscaled and the epilogue applies 1/|e|.
-  const bool cos_noscale = METRIC == RL_METRIC_COSINE && t.row_stats[2] > 0.f && t.row_stats[2] <= 2.f &&
-                           t.row_stats[1] <= 1024.f && t.row_stats[3] == 0.f;
+  const bool cos_noscale = METRIC == RL_METRIC_COSINE &&
+                           (EF16 || (t.row_stats[2] > 0.f && t.row_stats[2] <= 2.f && t.row_stats[1] <= 1024.f &&
+                                     t.row_stats[3] == 0.f));   // (the host only allows fp16 storage when this holds)
 
-  if (warp >= kFirstLoaderWarp) {
+  if (EF16 && warp >= kFirstLoaderWarp) {
+    // ===== corpus loaders, fp16 storage: HBM -> registers -> swizzled smem, no conversion =====
+    // A K slice of a row is 128 bytes = 8 chunks of 16 bytes; thread lt owns chunk lt & 7 of rows
+    // (lt >> 3) + 32 i.  Four items (4 x 16 KB per SM) stay in flight in registers.
+    const int lt = threadIdx.x - kFirstLoaderWarp * 32;
+    const int j = lt & 7, r0 = lt >> 3;
+    const __half* Eh = reinterpret_cast<const __half*>(a.E);
+    const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
+    const __half2 gs2 = __float2half2_rn(gscale);   // exact power of two (dot / l2 only)
+    const bool scale = gscale != 1.f;
+    const int64_t total_items = my_tiles * t.n_ks;
+    const size_t pitch32_bytes = (size_t)a.ld * 32 * sizeof(__half);
+    const size_t slice_bytes = kSliceK * sizeof(__half);
+    uint4 ring[4][4];
+    int64_t ld_tile = 0;
+    int ld_ks = 0, ld_rows = 0;
+    const unsigned char* ld_ptr = nullptr;
+    auto ld_set_tile = [&]() {
+      if (ld_tile < my_tiles && ord_of(ld_tile) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(ld_tile));
+        const int64_t rem = a.n_rows - blk * kTileM;
+        ld_rows = rem < kTileM ? (int)rem : kTileM;
+        ld_ptr = reinterpret_cast<const unsigned char*>(Eh + (size_t)(blk * kTileM + r0) * a.ld + j * 8);
+      } else {
+        ld_rows = 0;
+      }
+    };
+    int64_t pf_tile = 0;
+    int pf_ks = 0, pf_rows = 0;
+    const unsigned char* pf_ptr = nullptr;
+    auto pf_set_tile = [&]() {
+      if (pf_tile < my_tiles && ord_of(pf_tile) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(pf_tile));
+        const int64_t rem = a.n_rows - blk * kTileM;
+        pf_rows = rem < kTileM ? (int)rem : kTileM;
+        pf_ptr = reinterpret_cast<const unsigned char*>(Eh + (size_t)(blk * kTileM + (lt & 127)) * a.ld);
+        if (METRIC == RL_METRIC_COSINE && lt < 4 && lt * 32 < pf_rows) prefetch_l2(a.inv_norm + blk * kTileM + lt * 32);
+      } else {
+        pf_rows = 0;
+      }
+    };
+    auto prefetch_item = [&]() {   // one 128-byte line per row and item
+      if (lt < 128 && lt < pf_rows && pf_ks * kSliceK < a.d) prefetch_l2(pf_ptr);
+      pf_ptr += slice_bytes;
+      if (++pf_ks == t.n_ks) {
+        pf_ks = 0;
+        ++pf_tile;
+        pf_set_tile();
+      }
+    };
+    auto issue_item = [&](uint4 (&buf)[4]) {
+      const bool col_ok = ld_ks * kSliceK + j * 8 < a.d;
+      const unsigned char* p = ld_ptr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (col_ok && r0 + 32 * i < ld_rows) buf[i] = ldg_stream_u4(p);
+        else buf[i] = make_uint4(0u, 0u, 0u, 0u);
+        p += pitch32_bytes;
+      }
+      ld_ptr += slice_bytes;
+      if (++ld_ks == t.n_ks) {
+        ld_ks = 0;
+        ++ld_tile;
+        ld_set_tile();
+      }
+      prefetch_item();
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t sw_off = (uint32_t)r0 * 128u + (((uint32_t)j ^ ((uint32_t)r0 & 7u)) << 4);
+    auto process = [&](uint4 (&buf)[4]) {
+      mbar_wait(&s.empty[stage], phase ^ 1u);
+      unsigned char* A = s.stage_base + (size_t)stage * sbytes + sw_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 v = buf[i];
+        if (scale) {
+          __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gs2);
+        }
+        *reinterpret_cast<uint4*>(A + i * 32 * 128) = v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[stage]);
+      issue_item(buf);
+      if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+    };
+    ld_set_tile();
+    pf_set_tile();
+    for (int i = 0; i < 2 * kPrefetchItems; ++i) prefetch_item();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) issue_item(ring[r]);
+    for (int64_t item = 0; item < total_items; item += 4) {
+      process(ring[0]);
+      if (item + 1 < total_items) process(ring[1]);
+      if (item + 2 < total_items) process(ring[2]);
+      if (item + 3 < total_items) process(ring[3]);
+    }
+  } else if (warp >= kFirstLoaderWarp) {
     // ===== corpus loaders: HBM fp32 -> registers -> fp16 -> swizzled smem (UMMA A operand) =====
     const int lt = threadIdx.x - kFirstLoaderWarp * 32;  // 0..255
     const int c4 = lt & 15;                              // float4 column within the 64-wide K slice
@@ -423,15 +528,15 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             float key = __uint_as_float(select32(v, j));
             if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
             else key *= lane_scale;
-            // Stage the hit in shared memory; global slots are claimed once per (tile, query) at the flush.
+            // Stage the hit in shared memory (one returning atomic for the slot; the histogram update
+            // does not wait); per-query ranks and global slots are handed out in bulk at the flush.
             const int pos = atomicAdd(&s.list_n[0], 1);
             {
               const int hb = (c0 + j) * kHistBins + hist_bin(key, s.thr0[c0 + j], s.inv_w[c0 + j]);
               atomicAdd(&s.hist[hb >> 1], 1u << ((hb & 1) * 16));
             }
             if (pos < kListCap) {
-              const int rank = atomicAdd(&s.cnt[c0 + j], 1);
-              s.list[pos * 3 + 0] = (uint32_t)(c0 + j) | ((uint32_t)rank << 16);
+              s.list[pos * 3 + 0] = (uint32_t)(c0 + j);
               s.list[pos * 3 + 1] = __float_as_uint(key);
               s.list[pos * 3 + 2] = (uint32_t)row;
             } else {
@@ -473,6 +578,11 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
         if (do_flush) {
           flushed_once = true;
           const int n = min(n_all, kListCap);
+          for (int e = et; e < n; e += kNumEpiWarps * 32) {   // rank of every staged hit within its query
+            const int col = (int)s.list[e * 3 + 0];
+            s.list[e * 3 + 0] = (uint32_t)col | ((uint32_t)atomicAdd(&s.cnt[col], 1) << 16);
+          }
+          epi_bar_sync();
           for (int col = et; col < kMaxQ; col += kNumEpiWarps * 32) {
             const int c = s.cnt[col];
             if (c > 0) {
@@ -579,6 +689,7 @@ __global__ void __launch_bounds__(128) query_image_kernel(const float* __restric
 
 bool tcgen05_supported(const rl_scan_params* p) {
   if (p == nullptr || p->n_rows <= 0 || p->B <= 0) return false;
+  if (p->e_dtype == 1 && (p->d % 8 != 0 || p->ld % 8 != 0)) return false;
   if (p->d % 4 != 0 || p->ld % 4 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p->E) & 15) != 0) return false;
   if ((p->d + kSliceK - 1) / kSliceK > 1024) return false;
@@ -662,15 +773,15 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
       return RL_OK;
     };
     int rc;
-    if (pair) {
-      if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE, true>, true);
-      else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT, true>, true);
-      else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2, true>, true);
-    } else {
-      if (p->metric == RL_METRIC_COSINE) rc = launch(scan_tcgen05_kernel<RL_METRIC_COSINE, false>, false);
-      else if (p->metric == RL_METRIC_DOT) rc = launch(scan_tcgen05_kernel<RL_METRIC_DOT, false>, false);
-      else rc = launch(scan_tcgen05_kernel<RL_METRIC_L2, false>, false);
-    }
+    const bool f16 = p->e_dtype == 1;
+    auto dispatch = [&](auto metric_tag) -> int {
+      constexpr int M = decltype(metric_tag)::value;
+      if (pair) return f16 ? launch(scan_tcgen05_kernel<M, true, true>, true) : launch(scan_tcgen05_kernel<M, true, false>, true);
+      return f16 ? launch(scan_tcgen05_kernel<M, false, true>, false) : launch(scan_tcgen05_kernel<M, false, false>, false);
+    };
+    if (p->metric == RL_METRIC_COSINE) rc = dispatch(std::integral_constant<int, RL_METRIC_COSINE>{});
+    else if (p->metric == RL_METRIC_DOT) rc = dispatch(std::integral_constant<int, RL_METRIC_DOT>{});
+    else rc = dispatch(std::integral_constant<int, RL_METRIC_L2>{});
     if (rc != RL_OK) return rc;
   }
   return RL_OK;

@@ -5,6 +5,8 @@
 //
 // Reference semantics restated here: _search.py:75-79 (ORDER BY dist LIMIT num_hits) and
 // _search.py:143-150 (GROUP BY chunk_id, max(sim), ORDER BY sim DESC LIMIT num_results).
+#include <cuda_fp16.h>
+
 #include "select_finalize.cuh"
 
 namespace rl {
@@ -504,7 +506,19 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
     const int32_t row = rows[s];
     const float* e = f.E + (int64_t)row * f.ld;
     double dot = 0.0, ne = 0.0;
-    if (vec) {
+    if (f.e_f16) {   // float16 storage: 8 halves per 16-byte load (d % 8 == 0)
+      const __half* eh = reinterpret_cast<const __half*>(f.E) + (int64_t)row * f.ld;
+      for (int c = lane * 8; c < f.d; c += 256) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(eh + c));
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float2 ev = __half22float2(h[k2]);
+          dot += (double)ev.x * qv[c + 2 * k2] + (double)ev.y * qv[c + 2 * k2 + 1];
+          ne += (double)ev.x * ev.x + (double)ev.y * ev.y;
+        }
+      }
+    } else if (vec) {
       for (int c = lane * 4; c < f.d; c += 128) {
         const float4 ev = __ldg(reinterpret_cast<const float4*>(e + c));
         const float4 qq = *reinterpret_cast<const float4*>(qv + c);

@@ -304,3 +304,42 @@ def test_update_query_adapter_matches_oracle_fit(rl):
     _, s_on = rl.vector_search(evals[0][0], num_results=5, config=cfg)
     _, s_off = rl.vector_search(evals[0][0], num_results=5, config=rl.RAGLiteConfig(db_url="mem://fit", reranker=None, vector_search_query_adapter=False))
     assert s_on != s_off
+
+
+def test_index_from_chunk_embedding_rows(rl):
+    """The chunk_embedding table read in insertion order."""
+    E, off = make_corpus(50, (1, 5), 32, seed=71)
+    row_ids = [f"doc-{c // 7}-chunk-{c}" for c in ovs.row_to_chunk(off)]
+    idx = rl.CorpusIndex.from_chunk_embedding_rows(row_ids, E)
+    assert np.array_equal(idx.chunk_off, off) and idx.chunk_ids[3] == "doc-0-chunk-3"
+    cfg = rl.RAGLiteConfig(db_url="mem://rows", reranker=None)
+    rl.register_index(cfg, idx)
+    q = make_queries(E, 1, seed=72)[0]
+    ids, scores = rl.vector_search(q, num_results=4, config=cfg)
+    ref_ids, ref_sims, _ = ovs.vector_search_sql(E, off, q, num_results=4, f64=True)
+    assert ids == [f"doc-{c // 7}-chunk-{c}" for c in ref_ids] and np.allclose(scores, ref_sims, atol=1e-4)
+    with pytest.raises(ValueError):
+        rl.CorpusIndex.from_chunk_embedding_rows(["a", "b", "a"], E[:3])
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "l2"])
+def test_fp16_storage_matches_oracle(rl, metric):
+    """Lossless float16 corpus layout: RAGLite's embeddings are fp16-rounded (_embed.py:140)."""
+    E, off = make_corpus(3000, (1, 9), 128, seed=81, fp16_round=True)
+    Q = make_queries(E, 12, seed=82)
+    idx16 = rl.CorpusIndex(E, off, storage="fp16")
+    assert idx16.E.dtype.is_floating_point and idx16.E.element_size() == 2
+    cfg = rl.RAGLiteConfig(vector_search_distance_metric=metric, reranker=None)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=10, config=cfg, index=idx16)
+    ids2, sims2, counts2 = rl.vector_search_batch(Q, num_results=10, config=cfg, index=idx16, exact_maxsim=True)
+    for b in range(len(Q)):
+        check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=10, metric=metric)
+        check_exact_maxsim(E, off, Q[b], ids2[b, :counts2[b]], sims2[b, :counts2[b]], k=10, metric=metric)
+    st = idx16.scan_stats()
+    assert st["algo"] == 2
+
+
+def test_fp16_storage_rejects_lossy_input(rl):
+    E, off = make_corpus(100, 2, 64, seed=83)          # general float32 values: not representable
+    with pytest.raises(ValueError):
+        rl.CorpusIndex(E, off, storage="fp16")
