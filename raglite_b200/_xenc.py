@@ -10,6 +10,7 @@ LayerNorm, pooler+classifier) on packed variable-length batches -- no padding to
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from collections.abc import Sequence
 from pathlib import Path
 from typing import Any
@@ -123,6 +124,7 @@ class CrossEncoderEngine:
         w.cls_w, w.cls_b = cls_w.data_ptr(), cls_b.data_ptr()
         self.weights = w
         self._ws: torch.Tensor | None = None
+        self._lock = threading.Lock()   # reference callers rerank from thread pools (_rag.py:317)
 
     # ---- constructors ------------------------------------------------------------------------------
     @classmethod
@@ -178,14 +180,14 @@ class CrossEncoderEngine:
         dev = host.to(self.device, non_blocking=True)
         d_ids, d_types, d_pos, d_cu = dev[:T], dev[T:2 * T], dev[2 * T:3 * T], dev[3 * T:]
         out = torch.empty((2, P), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             need = int(self.lib.rl_xenc_workspace_bytes(C.byref(self.weights), T))
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             check(self.lib.rl_xenc_score(C.byref(self.weights), d_ids.data_ptr(), d_types.data_ptr(), d_pos.data_ptr(),
                                          d_cu.data_ptr(), P, T, int(lens.max()), out[0].data_ptr(), out[1].data_ptr(),
                                          self._ws.data_ptr(), self._ws.numel(), _stream()), "rl_xenc_score")
-        res = out.cpu().numpy()
+            res = out.cpu().numpy()   # (synchronises before the workspace can be reused by another thread)
         return res[0], res[1]
 
     def encode_pairs(self, queries: Sequence[str], docs: Sequence[str]) -> tuple[list[np.ndarray], list[np.ndarray]]:

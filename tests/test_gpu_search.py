@@ -343,3 +343,40 @@ def test_fp16_storage_rejects_lossy_input(rl):
     E, off = make_corpus(100, 2, 64, seed=83)          # general float32 values: not representable
     with pytest.raises(ValueError):
         rl.CorpusIndex(E, off, storage="fp16")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_block_boundaries_and_batch_groups(rl, algo):
+    """Rows exactly on / one past a 128-row block edge; batches of 1, 256 and 257 (two query groups)."""
+    _algo_ok(rl, algo, 64)
+    for n_rows in (128, 129, 256 * 3):
+        E, off = make_corpus(n_rows, 1, 64, seed=n_rows)
+        idx = rl.CorpusIndex(E, off)
+        for B in (1, 257):
+            Q = make_queries(E, B, seed=B)
+            ids, sims, counts = rl.vector_search_batch(Q, num_results=3, config=rl.RAGLiteConfig(reranker=None), index=idx, algo=algo)
+            for b in (0, B - 1):
+                check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=3)
+
+
+def test_zero_rows_and_k_larger_than_corpus(rl):
+    E, off = make_corpus(30, 2, 32, seed=91)
+    E[10] = 0.0                                            # an all-zero embedding row
+    idx = rl.CorpusIndex(E, off)
+    Q = make_queries(E, 3, seed=92)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=50, config=rl.RAGLiteConfig(reranker=None), index=idx,
+                                               exact_maxsim=True)
+    assert np.all(counts == 30) and np.all(np.isfinite(sims[:, :30]))
+    for b in range(3):
+        assert sorted(ids[b, :30].tolist()) == list(range(30))
+        assert np.all(np.diff(sims[b, :30]) <= 1e-6)
+
+
+def test_selection_larger_than_finalize_window_is_rejected(rl):
+    from raglite_b200._lib import RagliteB200Error
+
+    E, off = make_corpus(200, 40, 32, seed=93)             # 40 vectors per chunk
+    idx = rl.CorpusIndex(E, off)
+    Q = make_queries(E, 1, seed=94)
+    with pytest.raises((RagliteB200Error, ValueError)):
+        rl.vector_search_batch(Q, num_results=100, config=rl.RAGLiteConfig(reranker=None), index=idx, exact_maxsim=True)
