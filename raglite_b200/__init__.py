@@ -9,10 +9,20 @@ from ._config import RAGLiteConfig
 from ._embed import embed_strings, register_token_embedder
 from ._index import Chunk, CorpusIndex, get_index, merge_hits, register_index, unregister_index
 from ._query_adapter import reciprocal_rank_fusion, update_query_adapter
-from ._search import rerank_chunks, retrieve_chunks, vector_search, vector_search_batch
+from ._search import (
+    ChunkSpan,
+    rerank_chunks,
+    retrieve_chunk_spans,
+    retrieve_chunks,
+    search_and_rerank_chunk_spans,
+    search_and_rerank_chunks,
+    vector_search,
+    vector_search_batch,
+)
 
 __all__ = [
     "Chunk",
+    "ChunkSpan",
     "CorpusIndex",
     "RAGLiteConfig",
     "embed_strings",
@@ -22,7 +32,10 @@ __all__ = [
     "reciprocal_rank_fusion",
     "register_token_embedder",
     "rerank_chunks",
+    "retrieve_chunk_spans",
     "retrieve_chunks",
+    "search_and_rerank_chunk_spans",
+    "search_and_rerank_chunks",
     "unregister_index",
     "update_query_adapter",
     "vector_search",

@@ -184,3 +184,89 @@ def rerank_chunks(
         results = reranker.rank(query=query, docs=[str(chunk) for chunk in chunks])
         chunks = [chunks[result.doc_id] for result in results.results]
     return chunks
+
+
+# ---- the steps right after the hot path ------------------------------------------
+from dataclasses import dataclass as _dataclass  # noqa: E402
+
+
+@_dataclass
+class ChunkSpan:
+    """A run of consecutive chunks of one document (reference ``_database.py:326-398``)."""
+
+    chunks: list[Chunk]
+
+    @property
+    def document_id(self) -> str:
+        return self.chunks[0].document_id if self.chunks else ""
+
+    @property
+    def content(self) -> str:
+        """Front matter and heading of the first chunk, then all bodies (``_database.py:389-394``)."""
+        if not self.chunks:
+            return ""
+        bodies = "".join(chunk.body for chunk in self.chunks)
+        return f"{self.chunks[0].front_matter}\n\n{self.chunks[0].headings.strip()}\n\n{bodies}".strip()
+
+    def __str__(self) -> str:
+        return self.content
+
+
+def retrieve_chunk_spans(
+    chunk_ids: list[ChunkId] | list[Chunk], *, neighbors: tuple[int, ...] | None = (-1, 1),
+    config: RAGLiteConfig | None = None,
+) -> list[ChunkSpan]:
+    """Group chunks (plus their ``neighbors`` in the same document) into contiguous spans, ordered by
+    the summed reciprocal rank ``1 / (i + 1)`` of the chunks they contain (``_search.py:302-361``)."""
+    if not chunk_ids:
+        return []
+    config = config or RAGLiteConfig()
+    chunks: list[Chunk] = (
+        retrieve_chunks(chunk_ids, config=config)  # type: ignore[arg-type]
+        if all(isinstance(c, ChunkId) for c in chunk_ids) else list(chunk_ids)  # type: ignore[arg-type]
+    )
+    score = {chunk.id: 1 / (i + 1) for i, chunk in enumerate(chunks)}
+    pool: dict[tuple[str, int], Chunk] = {(c.document_id, c.index): c for c in chunks}
+    if neighbors:
+        index = get_index(config)
+        local = getattr(index, "local", index) if index is not None else None
+        table = {(c.document_id, c.index): c for c in (local.chunks or [])} if local is not None else {}
+        for c in chunks:
+            for off in neighbors:
+                nb = table.get((c.document_id, c.index + off))
+                if nb is not None:
+                    pool.setdefault((nb.document_id, nb.index), nb)
+    spans: list[ChunkSpan] = []
+    run: list[Chunk] = []
+    for key in sorted(pool):
+        c = pool[key]
+        if run and (c.document_id != run[-1].document_id or c.index != run[-1].index + 1):
+            spans.append(ChunkSpan(run))
+            run = []
+        run.append(c)
+    if run:
+        spans.append(ChunkSpan(run))
+    spans.sort(key=lambda s: sum(score.get(c.id, 0.0) for c in s.chunks), reverse=True)
+    return spans
+
+
+def search_and_rerank_chunks(  # noqa: PLR0913
+    query: str, *, num_results: int = 8, oversample: int = 4, search: Any = None,
+    config: RAGLiteConfig | None = None, metadata_filter: MetadataFilter | None = None,
+) -> list[Chunk]:
+    """Search ``oversample * num_results`` chunks, rerank, keep ``num_results`` (``_search.py:400-413``).
+    The reference defaults ``search`` to hybrid search; keyword search is out of scope here, so the
+    default is ``vector_search``."""
+    search = search or vector_search
+    chunk_ids, _ = search(query, num_results=oversample * num_results, metadata_filter=metadata_filter, config=config)
+    return rerank_chunks(query, chunk_ids, config=config)[:num_results]
+
+
+def search_and_rerank_chunk_spans(  # noqa: PLR0913
+    query: str, *, num_results: int = 8, oversample: int = 4, neighbors: tuple[int, ...] | None = (-1, 1),
+    search: Any = None, config: RAGLiteConfig | None = None, metadata_filter: MetadataFilter | None = None,
+) -> list[ChunkSpan]:
+    """``search_and_rerank_chunks`` followed by span collation (``_search.py:416-433``)."""
+    chunks = search_and_rerank_chunks(query, num_results=num_results, oversample=oversample, search=search,
+                                      config=config, metadata_filter=metadata_filter)
+    return retrieve_chunk_spans(chunks, neighbors=neighbors, config=config)

@@ -380,3 +380,24 @@ def test_selection_larger_than_finalize_window_is_rejected(rl):
     Q = make_queries(E, 1, seed=94)
     with pytest.raises((RagliteB200Error, ValueError)):
         rl.vector_search_batch(Q, num_results=100, config=rl.RAGLiteConfig(reranker=None), index=idx, exact_maxsim=True)
+
+
+def test_search_and_rerank_chunk_spans_pipeline(rl):
+    """vector_search -> rerank_chunks -> span collation over one registered index (the callers right
+    after the hot path, reference _search.py:400-433)."""
+    from raglite_b200._rerank import ScoreFnRanker
+
+    E, off = make_corpus(60, (1, 4), 32, seed=95)
+    n = len(off) - 1
+    chunks = [rl.Chunk(id=f"c{c}", document_id=f"doc{c // 10}", index=c % 10, body=f"body {c} " * (1 + c % 5)) for c in range(n)]
+    idx = rl.CorpusIndex(E, off, chunk_ids=[c.id for c in chunks], chunks=chunks)
+    cfg = rl.RAGLiteConfig(db_url="mem://spans", reranker=ScoreFnRanker(lambda q, docs: [len(d) for d in docs]))
+    rl.register_index(cfg, idx)
+    rl.register_token_embedder(cfg.embedder, FakeLlama(n_ctx=64, dim=32, seed=3))
+    spans = rl.search_and_rerank_chunk_spans("alpha beta gamma", num_results=4, oversample=2, config=cfg)
+    assert 1 <= len(spans) <= 4 * 3 and all(isinstance(s, rl.ChunkSpan) for s in spans)
+    for s in spans:                                        # contiguous runs of one document
+        assert len({c.document_id for c in s.chunks}) == 1
+        assert [c.index for c in s.chunks] == list(range(s.chunks[0].index, s.chunks[0].index + len(s.chunks)))
+    top = rl.search_and_rerank_chunks("alpha beta gamma", num_results=4, oversample=2, config=cfg)
+    assert len(top) == 4 and [len(str(c)) for c in top] == sorted((len(str(c)) for c in top), reverse=True)

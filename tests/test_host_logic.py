@@ -154,3 +154,18 @@ def test_reciprocal_rank_fusion_matches_definition():
     assert reciprocal_rank_fusion([]) == ([], [])
     with pytest.raises(ValueError):
         reciprocal_rank_fusion([["a"]], weights=[1.0, 2.0])
+
+
+def test_retrieve_chunk_spans_groups_and_ranks():
+    """Span collation (reference _search.py:302-361) on Chunk objects: neighbours come from the
+    registered table only when one exists, contiguous runs merge, order = summed reciprocal rank."""
+    from raglite_b200 import Chunk, RAGLiteConfig, retrieve_chunk_spans
+
+    mk = lambda d, i: Chunk(id=f"{d}-{i}", document_id=d, index=i, body=f"[{d}{i}]")  # noqa: E731
+    ranked = [mk("A", 5), mk("B", 2), mk("A", 6), mk("A", 9)]
+    spans = retrieve_chunk_spans(ranked, neighbors=None, config=RAGLiteConfig(db_url="mem://none", reranker=None))
+    got = [[c.id for c in s.chunks] for s in spans]
+    # A5+A6 merge (1 + 1/3), then B2 (1/2), then A9 (1/4)
+    assert got == [["A-5", "A-6"], ["B-2"], ["A-9"]]
+    assert str(spans[0]) == "[A5][A6]" and spans[0].document_id == "A"
+    assert retrieve_chunk_spans([], config=RAGLiteConfig(reranker=None)) == []
