@@ -138,6 +138,17 @@ typedef struct rl_scan_stats {
 } rl_scan_stats;
 int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream);
 
+/* Rank probe for the reference's rank-then-filter metadata branch (_search.py:122-143, which keeps the
+ * 1 000 000 nearest vectors before it applies the filter): counts[b] = number of rows of the shard
+ * (p->row_allowed honoured, normally the tombstone mask only) whose similarity to query b is at least
+ * sim_floor[b] (device float32 [B], in the units vector_search returns: 1 - dist).  The scan compares
+ * approximate keys, so `bound` picks the side of the bracket: +1 counts every row whose exact
+ * similarity can reach the floor (upper bound), -1 only rows that certainly do (lower bound), 0 the raw
+ * key comparison.  One pass over the corpus, nothing stored; p is the same struct rl_maxsim_topk takes
+ * and the workspace the same size.  counts is device int32 [B]. */
+int rl_maxsim_count_at_least(const rl_scan_params* p, const float* sim_floor, int bound, int32_t* counts,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device time in ms of the stages of the rl_maxsim_topk calls made with RL_FLAG_TIME_KERNELS on this
  * workspace since the previous read (average over up to 32 calls): ms[0] = prep, ms[1] = sample scan (dump), ms[2] = select, ms[3] = main scan (emit),
  * ms[4] = finalize.  CUDA events are recorded on the launching stream; the call synchronises on the

@@ -93,13 +93,17 @@ def vector_search_sql(  # noqa: PLR0913
     adapter: np.ndarray | None = None,
     allowed_chunks: np.ndarray | None = None,
     f64: bool = False,
+    filter_first_max: int = 100_000,
+    rank_first_limit: int = 1_000_000,
 ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Exact-scan restatement of ``vector_search`` (``_search.py:58-153``, no HNSW approximation).
 
     Steps: adapter apply -> per-row ``dist`` -> ``ORDER BY dist LIMIT num_hits`` (top vectors)
     -> ``GROUP BY chunk_id, max(sim)`` -> ``ORDER BY sim DESC LIMIT num_results``.
     ``allowed_chunks`` (bool ``[C]``) restates the filter-first metadata branch
-    (``_search.py:105-121``).  Ties are broken by row / chunk index (SQL leaves them unspecified).
+    (``_search.py:105-121``) when at most ``filter_first_max`` rows match, and the rank-then-filter
+    branch (``_search.py:122-143``: the ``rank_first_limit`` nearest rows, then the filter) otherwise.
+    Ties are broken by row / chunk index (SQL leaves them unspecified).
 
     Returns ``(chunk_index[int64], sim[float], hit_rows[int64])`` where ``hit_rows`` are the
     ``num_hits`` selected vector rows in ascending-distance order.
@@ -113,7 +117,12 @@ def vector_search_sql(  # noqa: PLR0913
     r2c = row_to_chunk(chunk_off, E.shape[0])
     rows = np.arange(E.shape[0])
     if allowed_chunks is not None:
-        rows = rows[np.asarray(allowed_chunks, dtype=bool)[r2c]]
+        row_ok = np.asarray(allowed_chunks, dtype=bool)[r2c]
+        if int(row_ok.sum()) <= filter_first_max:      # metadata_count <= 100_000 (_search.py:105)
+            rows = rows[row_ok]
+        else:                                          # ORDER BY dist LIMIT 1_000_000, then the filter
+            nearest = np.argsort(dist, kind="stable")[:rank_first_limit]
+            rows = np.sort(nearest[row_ok[nearest]])
     order = rows[np.argsort(dist[rows], kind="stable")][:num_hits]
     one = 1.0 if f64 else np.float32(1.0)
     sim = one - dist[order]

@@ -14,7 +14,7 @@ from typing import Any
 import torch
 import torch.distributed as dist
 
-from ._index import CorpusIndex, ScanResult, merge_hits
+from ._index import CorpusIndex, ScanResult, limit_hits_to_nearest, merge_hits
 
 
 def pack_hits(hit_sim: torch.Tensor, hit_chunk: torch.Tensor, hit_count: torch.Tensor) -> torch.Tensor:
@@ -76,15 +76,27 @@ class ShardedIndex:
 
     def search_device(self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
                       row_allowed: torch.Tensor | None = None, checked: bool = True, flags: int = 0,
-                      sample_stride: int = 0) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                      sample_stride: int = 0, rank_first_limit: int | None = None
+                      ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Scan the local shard, all-gather, merge.  Everything stays on the device / current stream
-        (``checked=True`` adds the host-side overflow check and retry)."""
+        (``checked=True`` adds the host-side overflow check and retry).  ``rank_first_limit`` applies the
+        rank-then-filter metadata branch to the gathered lists (``limit_hits_to_nearest``)."""
         fn = self.local.scan_checked if checked else self.local.scan
         res: ScanResult = fn(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=row_allowed, flags=flags,
                              sample_stride=sample_stride)
         self.last_status = res.status
         sim, chunk, count = gather_hits(res.hit_sim, res.hit_chunk, res.hit_count, self.group)
+        if rank_first_limit is not None:
+            count = limit_hits_to_nearest(self, Q, sim, count, k=k, num_hits=num_hits, metric=metric, algo=algo,
+                                          limit=rank_first_limit)
         return merge_hits(sim, chunk, count, num_hits=num_hits, k=k)
+
+    def sum_over_shards(self, x: torch.Tensor) -> torch.Tensor:
+        """All-reduce (sum) of a small per-query tensor: row counts of the rank-then-filter probe."""
+        if self.group is not None and self.world > 1:
+            x = x.clone()
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+        return x
 
     def chunk_id_of(self, global_chunk: int) -> str:
         if self.global_chunk_ids is not None:

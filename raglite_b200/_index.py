@@ -10,6 +10,11 @@ Layout in HBM (one shard per GPU, rows of a chunk contiguous as the reference in
     chunk_off  int64   [C + 1] (host)        -- CSR offsets
     chunk_ids  list[str] (host)              -- ``chunk.id`` strings handed back to the caller
 
+The index follows the table as the reference mutates it: ``append_chunk_embedding_rows`` mirrors the
+flushes of ``insert_documents`` (``_insert.py:247-255``), ``delete_chunks`` / ``delete_documents`` the cascade of
+``delete_documents`` (``_delete.py:146-152``).  Deletes are tombstones (a per-row byte the scan already
+reads for metadata filters); ``compact`` drops them physically, in place.
+
 The registry maps ``RAGLiteConfig.db_url`` to an index, which is how the drop-in ``vector_search``
 finds its corpus given only a config (the reference opens the database named by ``db_url``).
 """
@@ -36,6 +41,26 @@ def _stream() -> int:
 
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else int(t.data_ptr())
+
+
+def csr_from_row_chunk_ids(ids: Sequence[ChunkId], known: set[ChunkId] | None = None) -> tuple[np.ndarray, list[ChunkId]]:
+    """Consecutive equal ``chunk_id`` values form one CSR segment (a chunk's vectors are inserted
+    contiguously, ``_insert.py:247-251``).  A chunk id that re-appears after another chunk, or that is
+    already ``known`` to the index, is a layout error."""
+    ids = list(ids)
+    offsets, chunk_ids, seen = [0], [], set()
+    for i, cid in enumerate(ids):
+        if i == 0 or cid != ids[i - 1]:
+            if cid in seen or (known is not None and cid in known):
+                raise ValueError(f"chunk_id {cid!r} is not contiguous in the chunk_embedding rows")
+            seen.add(cid)
+            chunk_ids.append(cid)
+            if i:
+                offsets.append(i)
+    offsets.append(len(ids))
+    if not ids:
+        offsets = [0]
+    return np.asarray(offsets, dtype=np.int64), chunk_ids
 
 
 @dataclass
@@ -105,19 +130,7 @@ class CorpusIndex:
         if storage not in ("fp32", "fp16"):
             raise ValueError("storage must be 'fp32' or 'fp16'")
         self.storage = storage
-        if storage == "fp16":
-            # Lossless only: RAGLite's embeddings are fp16-rounded already (_embed.py:140) and DuckDB merely
-            # widens them to FLOAT[d]; anything else must stay float32.
-            Eh = E.to(device=self.device, dtype=torch.float16).contiguous()
-            if E.dtype != torch.float16:
-                step = 1 << 20
-                for r0 in range(0, int(E.shape[0]), step):
-                    blk = E[r0:r0 + step].to(self.device, dtype=torch.float32)
-                    if not torch.equal(Eh[r0:r0 + step].float(), blk):
-                        raise ValueError("storage='fp16' needs embeddings that are exactly representable in float16")
-            self.E = Eh
-        else:
-            self.E = E.to(device=self.device, dtype=torch.float32).contiguous()
+        self.E = self._to_storage(E)
         self.n_rows, self.d = int(self.E.shape[0]), int(self.E.shape[1])
         if storage == "fp16" and self.d % 8:
             raise ValueError("storage='fp16' needs d % 8 == 0")
@@ -138,6 +151,10 @@ class CorpusIndex:
             raise ValueError("chunk_ids must have one entry per chunk")
         self.chunks = list(chunks) if chunks is not None else None
         self.chunk_metadata = list(chunk_metadata) if chunk_metadata is not None else None
+        self._alive: torch.Tensor | None = None        # uint8 [n_rows]; None = no tombstones
+        self._bufs: dict[str, torch.Tensor] | None = None  # owned capacity buffers once the index has grown
+        self._chunk_alive = np.ones(self.n_chunks, dtype=bool)
+        self._chunk_pos: dict[ChunkId, int] | None = None
         self.query_adapter: np.ndarray | None = None  # IndexMetadata["default"]["query_adapter"]
         self._adapter_dev: torch.Tensor | None = None
         self._ws: torch.Tensor | None = None
@@ -149,15 +166,11 @@ class CorpusIndex:
             self.stats = torch.zeros(4, dtype=torch.float32, device=self.device)
             self.row_chunk = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
             off_dev = torch.from_numpy(self.chunk_off).to(self.device)
-            stats_fn = self.lib.rl_row_stats_f16 if storage == "fp16" else self.lib.rl_row_stats
-            check(stats_fn(_ptr(self.E), self.n_rows, self.d, self.d, _ptr(self.inv_norm),
-                           _ptr(self.sq_norm), _ptr(self.stats), _stream()), "rl_row_stats")
+            self._row_stats(self.E, self.inv_norm, self.sq_norm)
             check(self.lib.rl_chunk_row_map(_ptr(off_dev), self.n_chunks, _ptr(self.row_chunk), _stream()),
                   "rl_chunk_row_map")
             torch.cuda.current_stream().synchronize()
-            if storage == "fp16" and self.n_rows:
-                st = self.stats.cpu().numpy()
-                self._fp16_cosine_ok = bool(0.0 < st[2] <= 2.0 and st[1] <= 1024.0 and st[3] == 0.0)
+            self._refresh_fp16_flag()
 
     @classmethod
     def from_chunk_embedding_rows(cls, row_chunk_ids: Sequence[ChunkId], embeddings: torch.Tensor | np.ndarray,
@@ -170,19 +183,211 @@ class CorpusIndex:
         E = torch.as_tensor(embeddings)
         if len(ids) != int(E.shape[0]):
             raise ValueError("one chunk_id per embedding row is required")
-        offsets, chunk_ids, seen = [0], [], set()
-        for i, cid in enumerate(ids):
-            if i == 0 or cid != ids[i - 1]:
-                if cid in seen:
-                    raise ValueError(f"chunk_id {cid!r} is not contiguous in the chunk_embedding rows")
-                seen.add(cid)
-                chunk_ids.append(cid)
-                if i:
-                    offsets.append(i)
-        offsets.append(len(ids))
-        if not ids:
-            offsets = [0]
-        return cls(E, np.asarray(offsets, dtype=np.int64), chunk_ids=chunk_ids, **kw)
+        offsets, chunk_ids = csr_from_row_chunk_ids(ids)
+        return cls(E, offsets, chunk_ids=chunk_ids, **kw)
+
+    def _to_storage(self, E: torch.Tensor) -> torch.Tensor:
+        """Rows in the index's storage dtype on its device.  ``fp16`` storage is lossless only: RAGLite's
+        embeddings are fp16-rounded already (``_embed.py:140``) and DuckDB merely widens them to FLOAT[d];
+        anything else must stay float32."""
+        if self.storage == "fp32":
+            return E.to(device=self.device, dtype=torch.float32).contiguous()
+        Eh = E.to(device=self.device, dtype=torch.float16).contiguous()
+        if E.dtype != torch.float16:
+            step = 1 << 20
+            for r0 in range(0, int(E.shape[0]), step):
+                blk = E[r0:r0 + step].to(self.device, dtype=torch.float32)
+                if not torch.equal(Eh[r0:r0 + step].float(), blk):
+                    raise ValueError("storage='fp16' needs embeddings that are exactly representable in float16")
+        return Eh
+
+    # ---- mutation: the index follows the chunk_embedding table --------------------------------------
+    @property
+    def n_live_chunks(self) -> int:
+        return int(self._chunk_alive.sum())
+
+    @property
+    def live_chunks(self) -> list[Chunk]:
+        """``Chunk`` records that have not been deleted."""
+        if self.chunks is None:
+            return []
+        return [c for c, ok in zip(self.chunks, self._chunk_alive, strict=True) if ok]
+
+    def _row_stats(self, E: torch.Tensor, inv_norm: torch.Tensor, sq_norm: torch.Tensor) -> None:
+        stats_fn = self.lib.rl_row_stats_f16 if self.storage == "fp16" else self.lib.rl_row_stats
+        check(stats_fn(_ptr(E), int(E.shape[0]), self.d, self.d, _ptr(inv_norm), _ptr(sq_norm), _ptr(self.stats),
+                       _stream()), "rl_row_stats")
+
+    def _refresh_fp16_flag(self) -> None:
+        if self.storage == "fp16" and self.n_rows:
+            st = self.stats.cpu().numpy()
+            self._fp16_cosine_ok = bool(0.0 < st[2] <= 2.0 and st[1] <= 1024.0 and st[3] == 0.0)
+
+    def reserve(self, n_rows: int) -> None:
+        """Pre-size the row buffers (size HBM for the final corpus once instead of re-growing per flush)."""
+        with self._lock, torch.cuda.device(self.device):
+            self._reserve(int(n_rows))
+
+    _ROW_ARRAYS = ("E", "inv_norm", "sq_norm", "row_chunk")
+
+    def _reserve(self, n_rows: int) -> None:
+        """Make the owned capacity buffers hold ``n_rows`` rows; the public arrays stay views of their
+        first ``self.n_rows`` rows.  (The constructor adopts the caller's tensor without a copy, so the
+        first growth is also the point where the index starts owning its storage.)"""
+        cap = int(self._bufs["E"].shape[0]) if self._bufs is not None else -1
+        if n_rows <= cap:
+            return
+        new_cap = max(n_rows, self.n_rows + self.n_rows // 2 + 1024)
+        bufs = {}
+        for name in self._ROW_ARRAYS:
+            t = getattr(self, name)
+            bufs[name] = torch.empty((new_cap, *t.shape[1:]), dtype=t.dtype, device=self.device)
+            bufs[name][: self.n_rows] = t
+            setattr(self, name, bufs[name][: self.n_rows])
+        self._bufs = bufs
+
+    def append(  # noqa: PLR0913
+        self, embeddings: torch.Tensor | np.ndarray, chunk_offsets: np.ndarray | Sequence[int] | None = None, *,
+        vecs_per_chunk: int | None = None, chunk_ids: Sequence[ChunkId] | None = None,
+        chunks: Sequence[Chunk] | None = None, chunk_metadata: Sequence[dict[str, Any]] | None = None,
+    ) -> None:
+        """Append whole chunks (rows of a chunk contiguous) behind the resident rows: one flush of
+        ``insert_documents`` (``_insert.py:247-255``).  Only the new rows are read: their norms are
+        computed by ``rl_row_stats``, which folds their maxima into the shard statistics."""
+        E = torch.as_tensor(embeddings)
+        if E.ndim != 2 or int(E.shape[1]) != self.d:
+            raise ValueError(f"embeddings must be [n_rows, {self.d}]")
+        m = int(E.shape[0])
+        if chunk_offsets is None:
+            v = 1 if vecs_per_chunk is None else int(vecs_per_chunk)
+            if m % v:
+                raise ValueError("n_rows is not a multiple of vecs_per_chunk")
+            chunk_offsets = np.arange(0, m + 1, v, dtype=np.int64)
+        off = np.ascontiguousarray(np.asarray(chunk_offsets, dtype=np.int64))
+        if off[0] != 0 or off[-1] != m or np.any(np.diff(off) < 0):
+            raise ValueError("chunk_offsets must be a CSR offset array covering all rows")
+        c_new = len(off) - 1
+        for name, given in (("chunk_ids", chunk_ids), ("chunks", chunks), ("chunk_metadata", chunk_metadata)):
+            tracked = getattr(self, name) is not None
+            if tracked and given is None:
+                raise ValueError(f"the index tracks {name}: pass one per appended chunk")
+            if given is not None and not tracked and self.n_chunks:
+                raise ValueError(f"the index holds no {name}; it cannot start tracking them on append")
+            if given is not None and len(given) != c_new:
+                raise ValueError(f"{name} must have one entry per appended chunk")
+        if chunk_ids is not None:
+            known = self._positions()
+            for cid in chunk_ids:   # a deleted chunk may come back (re-inserting a document re-creates its ids)
+                if cid in known and self._chunk_alive[known[cid]]:
+                    raise ValueError(f"chunk_id {cid!r} is already in the index")
+        if m == 0:
+            return
+        with self._lock, torch.cuda.device(self.device):
+            rows = self._to_storage(E)
+            n0 = self.n_rows
+            self._reserve(n0 + m)
+            for name in self._ROW_ARRAYS:
+                setattr(self, name, self._bufs[name][: n0 + m])
+            self.E[n0:] = rows
+            self._row_stats(self.E[n0:], self.inv_norm[n0:], self.sq_norm[n0:])
+            counts = torch.from_numpy(np.diff(off)).to(self.device)
+            owners = torch.arange(self.n_chunks, self.n_chunks + c_new, dtype=torch.int32, device=self.device)
+            self.row_chunk[n0:] = torch.repeat_interleave(owners, counts)
+            if self._alive is not None:
+                self._alive = torch.cat([self._alive, torch.ones(m, dtype=torch.uint8, device=self.device)])
+            self.chunk_off = np.concatenate([self.chunk_off, off[1:] + n0])
+            self._chunk_alive = np.concatenate([self._chunk_alive, np.ones(c_new, dtype=bool)])
+            for name, given in (("chunk_ids", chunk_ids), ("chunks", chunks), ("chunk_metadata", chunk_metadata)):
+                if given is not None:
+                    setattr(self, name, (getattr(self, name) or []) + list(given))
+            if chunk_ids is not None and self._chunk_pos is not None:
+                self._chunk_pos.update({cid: self.n_chunks + i for i, cid in enumerate(chunk_ids)})
+            self.n_rows, self.n_chunks = n0 + m, self.n_chunks + c_new
+            self.max_vecs = max(self.max_vecs, int(np.diff(off).max()))
+            torch.cuda.current_stream().synchronize()
+            self._refresh_fp16_flag()
+
+    def append_chunk_embedding_rows(self, row_chunk_ids: Sequence[ChunkId], embeddings: torch.Tensor | np.ndarray,
+                                    **kw: Any) -> None:
+        """``append`` for rows spelled like the table: one ``chunk_id`` per embedding row."""
+        ids = list(row_chunk_ids)
+        if len(ids) != int(torch.as_tensor(embeddings).shape[0]):
+            raise ValueError("one chunk_id per embedding row is required")
+        offsets, chunk_ids = csr_from_row_chunk_ids(ids)
+        self.append(embeddings, offsets, chunk_ids=chunk_ids, **kw)
+
+    def _positions(self) -> dict[ChunkId, int]:
+        if self._chunk_pos is None:
+            self._chunk_pos = {cid: i for i, cid in enumerate(self.chunk_ids or [])}
+        return self._chunk_pos
+
+    def delete_chunks(self, chunk_ids: Sequence[ChunkId]) -> int:
+        """Tombstone the rows of the given chunks (``DELETE FROM chunk_embedding WHERE chunk_id IN ...``,
+        the cascade of ``_delete.py:146-152``); unknown or already deleted ids are ignored.  Returns the
+        number of chunks removed.  Chunk indices stay stable until ``compact``."""
+        if self.chunk_ids is None:
+            raise ValueError("the index holds no chunk ids")
+        pos = self._positions()
+        local = sorted({pos[c] for c in chunk_ids if c in pos and self._chunk_alive[pos[c]]})
+        return self._delete_local(np.asarray(local, dtype=np.int64))
+
+    def delete_documents(self, document_ids: Sequence[str]) -> int:
+        """Tombstone every chunk of the given documents (``_delete.py:146-152``)."""
+        if self.chunks is None:
+            raise ValueError("the index holds no Chunk records (document ids unknown)")
+        wanted = set(document_ids)
+        local = [i for i, c in enumerate(self.chunks) if c.document_id in wanted and self._chunk_alive[i]]
+        return self._delete_local(np.asarray(local, dtype=np.int64))
+
+    def _delete_local(self, local: np.ndarray) -> int:
+        if len(local) == 0:
+            return 0
+        lo, hi = self.chunk_off[local], self.chunk_off[local + 1]
+        rows = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in zip(lo, hi, strict=True)]) if len(local) else lo
+        with self._lock, torch.cuda.device(self.device):
+            if self._alive is None:
+                self._alive = torch.ones(self.n_rows, dtype=torch.uint8, device=self.device)
+            if len(rows):
+                self._alive.index_fill_(0, torch.from_numpy(rows).to(self.device), 0)
+            self._chunk_alive[local] = False
+        return int(len(local))
+
+    def compact(self, block_rows: int = 1 << 20) -> None:
+        """Drop tombstoned rows physically: surviving rows slide down in place, block by block (a staged
+        block is at most ``block_rows`` rows, so the corpus never needs a second copy in HBM).  Chunk
+        indices are renumbered -- on a sharded corpus re-derive ``chunk_base`` of the later shards."""
+        if self._alive is None:
+            return
+        with self._lock, torch.cuda.device(self.device):
+            dst = 0
+            for r0 in range(0, self.n_rows, block_rows):
+                r1 = min(self.n_rows, r0 + block_rows)
+                idx = torch.nonzero(self._alive[r0:r1], as_tuple=False).flatten()
+                n_keep = int(idx.numel())
+                if n_keep and not (dst == r0 and n_keep == r1 - r0):
+                    self.E[dst:dst + n_keep] = self.E[r0:r1].index_select(0, idx)   # staged copy; lands below r0 + n_keep
+                dst += n_keep
+            keep = self._chunk_alive
+            counts = np.diff(self.chunk_off)[keep]
+            self.chunk_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            assert int(self.chunk_off[-1]) == dst
+            for name in ("chunk_ids", "chunks", "chunk_metadata"):
+                have = getattr(self, name)
+                if have is not None:
+                    setattr(self, name, [x for x, ok in zip(have, keep, strict=True) if ok])
+            self.n_rows, self.n_chunks = dst, int(keep.sum())
+            self.max_vecs = int(counts.max()) if len(counts) else 1
+            self._chunk_alive = np.ones(self.n_chunks, dtype=bool)
+            self._chunk_pos, self._alive = None, None
+            for name in self._ROW_ARRAYS:
+                setattr(self, name, getattr(self, name)[:dst])
+            self.stats.zero_()
+            self._row_stats(self.E, self.inv_norm, self.sq_norm)
+            off_dev = torch.from_numpy(self.chunk_off).to(self.device)
+            check(self.lib.rl_chunk_row_map(_ptr(off_dev), self.n_chunks, _ptr(self.row_chunk), _stream()),
+                  "rl_chunk_row_map")
+            torch.cuda.current_stream().synchronize()
+            self._refresh_fp16_flag()
 
     # ---- query adapter (IndexMetadata.get("default")["query_adapter"], _search.py:60) ------------
     def set_query_adapter(self, A: np.ndarray | None) -> None:
@@ -234,6 +439,8 @@ class CorpusIndex:
         B = int(Q.shape[0])
         H = num_hits if num_hits > 0 else k
         with self._lock, torch.cuda.device(self.device):
+            if self._alive is not None:  # tombstoned rows are masked like a metadata filter
+                row_allowed = self._alive if row_allowed is None else (row_allowed & self._alive)
             p = self._params(Q, k, num_hits, metric, algo, row_allowed, flags, sample_stride, cand_cap)
             need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
             if need == 0 and B > 0:
@@ -252,6 +459,36 @@ class CorpusIndex:
                   "rl_maxsim_topk")
             self.last_params = p
         return out
+
+    def count_at_least(  # noqa: PLR0913
+        self, Q: torch.Tensor, sim_floor: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine",
+        algo: str = "auto", bound: int = 1,
+    ) -> torch.Tensor:
+        """``rl_maxsim_count_at_least``: per query, how many live rows of the shard have a similarity of at
+        least ``sim_floor[b]`` (``bound=+1``: upper bound of the exact count, ``-1``: lower bound, ``0``:
+        raw approximate keys).  One pass over the corpus on the current stream; int32 ``[B]`` on device."""
+        if Q.dtype != torch.float32 or Q.ndim != 2 or Q.shape[1] != self.d or not Q.is_contiguous():
+            raise ValueError(f"Q must be a contiguous float32 [B, {self.d}] tensor")
+        B = int(Q.shape[0])
+        floor = sim_floor.to(device=self.device, dtype=torch.float32).contiguous()
+        if floor.shape != (B,):
+            raise ValueError("sim_floor must be [B]")
+        counts = torch.zeros(B, dtype=torch.int32, device=self.device)
+        with self._lock, torch.cuda.device(self.device):
+            p = self._params(Q, k, num_hits, metric, algo, self._alive, 0, 0, 0)
+            need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
+            if need == 0 and B > 0:
+                raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            check(self.lib.rl_maxsim_count_at_least(C.byref(p), _ptr(floor), int(bound), _ptr(counts), _ptr(self._ws),
+                                                    self._ws.numel(), _stream()), "rl_maxsim_count_at_least")
+        return counts
+
+    def sum_over_shards(self, x: torch.Tensor) -> torch.Tensor:
+        """A single shard is the whole corpus (``ShardedIndex`` all-reduces)."""
+        return x
 
     def scan_stats(self) -> dict[str, int]:
         """Counters of the last scan (synchronises)."""
@@ -313,6 +550,51 @@ def merge_hits(  # noqa: PLR0913
         check(lib.rl_topk_merge(_ptr(hs), _ptr(hc), _ptr(hn), R, B, H, num_hits, k, _ptr(out_sim), _ptr(out_chunk),
                                 _ptr(out_count), _stream()), "rl_topk_merge")
     return out_sim, out_chunk, out_count
+
+
+def limit_hits_to_nearest(  # noqa: PLR0913
+    index: Any, Q: torch.Tensor, hit_sim: torch.Tensor, hit_count: torch.Tensor, *, k: int, num_hits: int, metric: str,
+    algo: str = "auto", limit: int = 1_000_000, bisect_steps: int = 26,
+) -> torch.Tensor:
+    """The rank-then-filter metadata branch (``_search.py:122-143``): of the filtered hits only those among
+    the ``limit`` nearest vectors of the WHOLE corpus count.  ``hit_sim`` / ``hit_count`` are the gathered
+    filter-first hit lists ``[R, B, H]`` / ``[R, B]`` (descending per list); returns the counts to keep.
+
+    One counting pass proves the common case: if at most ``limit`` rows can be as near as the worst of
+    the ``num_hits`` best filtered hits, the filter-first answer already is the answer.  Otherwise the
+    similarity of the ``limit``-th nearest row is located by bisection over counting passes (raw
+    approximate keys: rows within the key error of that similarity may land on either side -- the
+    reference's HNSW scan is approximate at the same place)."""
+    local: CorpusIndex = getattr(index, "local", index)
+    R, B, H = (int(x) for x in hit_sim.shape)
+    valid = torch.arange(H, device=hit_sim.device)[None, None, :] < hit_count[:, :, None]
+    flat = torch.where(valid, hit_sim, hit_sim.new_full((), float("-inf"))).permute(1, 0, 2).reshape(B, R * H)
+    top = flat.topk(min(num_hits, R * H), dim=1).values
+    n_valid = hit_count.sum(0).clamp(max=top.shape[1]).to(torch.int64)
+    floor = top.gather(1, (n_valid - 1).clamp(min=0)[:, None])[:, 0]
+    floor = torch.where(n_valid > 0, floor, floor.new_full((), float("inf")))
+    kw = {"k": k, "num_hits": num_hits, "metric": metric}
+    ub = index.sum_over_shards(local.count_at_least(Q, floor, algo=algo, bound=1, **kw).to(torch.int64))
+    need = torch.nonzero(ub > limit).flatten()
+    if need.numel() == 0:
+        return hit_count
+    # bisection on the similarity of the limit-th nearest row, for the queries that need it
+    Qn = Q[need].contiguous()
+    lo = floor[need].clone()
+    qn = Qn.double().norm(dim=1)
+    max_norm = float(local.stats[0])
+    hi = (1.0 + qn * max_norm * 1.001 + 1e-3).float() if metric == "dot" else torch.full_like(lo, 1.0 + 1e-3)
+    exact_algo = "fp32" if local.storage == "fp32" else algo   # tightest keys this storage allows
+    for _ in range(bisect_steps):
+        mid = (lo + hi) * 0.5
+        c = index.sum_over_shards(local.count_at_least(Qn, mid, algo=exact_algo, bound=0, **kw).to(torch.int64))
+        ge = c >= limit
+        lo = torch.where(ge, mid, lo)
+        hi = torch.where(ge, hi, mid)
+    tau = torch.full((B,), float("-inf"), device=hit_sim.device)
+    tau[need] = lo
+    keep = (valid & (hit_sim >= tau[None, :, None])).sum(-1).to(hit_count.dtype)
+    return torch.minimum(hit_count, keep)
 
 
 # ---- registry: RAGLiteConfig.db_url -> index ---------------------------------------------------------

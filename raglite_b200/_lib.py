@@ -22,7 +22,7 @@ RL_MAX_SURVIVORS = 4096
 
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
-    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_copy_dump", "rl_topk_merge",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_copy_dump", "rl_topk_merge",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
@@ -79,6 +79,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_maxsim_workspace_bytes.argtypes = [C.POINTER(ScanParams)]
     lib.rl_maxsim_workspace_bytes.restype = C.c_size_t
     lib.rl_maxsim_topk.argtypes = [C.POINTER(ScanParams), vp, vp, vp, vp, vp, C.c_size_t, vp]
+    lib.rl_maxsim_count_at_least.argtypes = [C.POINTER(ScanParams), vp, C.c_int, vp, vp, C.c_size_t, vp]
     lib.rl_maxsim_stats.argtypes = [C.POINTER(ScanParams), vp, C.POINTER(ScanStats), vp]
     lib.rl_maxsim_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.rl_maxsim_copy_dump.argtypes = [C.POINTER(ScanParams), vp, vp, C.POINTER(C.c_int64), vp]

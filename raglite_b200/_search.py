@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from ._config import RAGLiteConfig
-from ._index import Chunk, CorpusIndex, get_index, merge_hits
+from ._index import Chunk, CorpusIndex, get_index, limit_hits_to_nearest, merge_hits
 from ._typing import ChunkId, FloatVector, MetadataFilter
 
 REFERENCE_CHUNK_MAX_SIZE = 2048  # RAGLiteConfig.chunk_max_size class default (_config.py:67)
@@ -34,9 +34,13 @@ def _adapt_metadata(metadata_filter: MetadataFilter | None) -> dict[str, list[An
     return {k: (list(v) if isinstance(v, (list, tuple)) else [v]) for k, v in metadata_filter.items()}
 
 
+FILTER_FIRST_MAX_ROWS = 100_000   # metadata_count <= 100_000: filter, then rank (_search.py:105)
+RANK_FIRST_LIMIT = 1_000_000      # otherwise: the 1_000_000 nearest vectors, then the filter (_search.py:126)
+
+
 def _allowed_rows(index: Any, metadata_filter: dict[str, list[Any]] | None) -> torch.Tensor | None:
-    """Filter-first branch (``_search.py:105-121``): rows whose chunk metadata contains every
-    requested value (JSON containment on list-valued metadata)."""
+    """Rows whose chunk metadata contains every requested value (JSON containment on list-valued
+    metadata, ``_search.py:82-95``) as the byte mask the scan reads."""
     if not metadata_filter:
         return None
     local: CorpusIndex = getattr(index, "local", index)
@@ -86,7 +90,7 @@ def vector_search_batch(  # noqa: PLR0913
         raise ValueError("queries must be [B, d]")
     k = int(num_results)
     B = int(Q.shape[0])
-    if local.n_chunks == 0 and not hasattr(index, "search_device"):
+    if local.n_live_chunks == 0 and not hasattr(index, "search_device"):
         return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
     if config.vector_search_query_adapter and local.query_adapter is not None:
         Q = local.apply_adapter(Q, round_fp16=queries_are_fp16)
@@ -95,12 +99,26 @@ def vector_search_batch(  # noqa: PLR0913
         return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
     allowed = _allowed_rows(index, _adapt_metadata(metadata_filter))
     metric = config.vector_search_distance_metric
+    # Which metadata branch the reference would take (_search.py:96-143): many matching rows in a corpus
+    # of more than 1M vectors -> only filtered hits among the 1M nearest vectors overall count.
+    rank_first_limit = None
+    if allowed is not None and num_hits > 0:
+        live = local._alive   # tombstones, if any
+        n_match = (allowed if live is None else allowed & live).sum(dtype=torch.int64)
+        n_rows = live.sum(dtype=torch.int64) if live is not None else torch.tensor(local.n_rows, device=local.device)
+        totals = index.sum_over_shards(torch.stack([n_match, n_rows.to(torch.int64)])).tolist()
+        if totals[0] > FILTER_FIRST_MAX_ROWS and totals[1] > RANK_FIRST_LIMIT:
+            rank_first_limit = RANK_FIRST_LIMIT
     if hasattr(index, "search_device"):  # sharded across ranks
         sim, chunk, count = index.search_device(Q, k=k, num_hits=num_hits, metric=metric, algo=algo,
-                                                row_allowed=allowed, checked=True)
+                                                row_allowed=allowed, checked=True, rank_first_limit=rank_first_limit)
     else:
         res = local.scan_checked(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=allowed)
-        sim, chunk, count = merge_hits(res.hit_sim, res.hit_chunk, res.hit_count, num_hits=num_hits, k=k)
+        hit_count = res.hit_count
+        if rank_first_limit is not None:
+            hit_count = limit_hits_to_nearest(local, Q, res.hit_sim[None], hit_count[None], k=k, num_hits=num_hits,
+                                              metric=metric, algo=algo, limit=rank_first_limit)[0]
+        sim, chunk, count = merge_hits(res.hit_sim, res.hit_chunk, hit_count, num_hits=num_hits, k=k)
     return chunk.cpu().numpy(), sim.cpu().numpy(), count.cpu().numpy()
 
 
@@ -146,7 +164,7 @@ def retrieve_chunks(chunk_ids: Sequence[ChunkId], *, config: RAGLiteConfig | Non
     local = getattr(index, "local", index) if index is not None else None
     if local is None or local.chunks is None:
         raise ValueError("The registered index holds no chunk texts")
-    by_id = {c.id: c for c in local.chunks}
+    by_id = {c.id: c for c in local.live_chunks}
     return [by_id[cid] for cid in chunk_ids if cid in by_id]
 
 
@@ -230,7 +248,7 @@ def retrieve_chunk_spans(
     if neighbors:
         index = get_index(config)
         local = getattr(index, "local", index) if index is not None else None
-        table = {(c.document_id, c.index): c for c in (local.chunks or [])} if local is not None else {}
+        table = {(c.document_id, c.index): c for c in local.live_chunks} if local is not None else {}
         for c in chunks:
             for off in neighbors:
                 nb = table.get((c.document_id, c.index + off))

@@ -277,6 +277,67 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   return rc;
 }
 
+extern "C" int rl_maxsim_count_at_least(const rl_scan_params* p, const float* sim_floor, int bound, int32_t* counts,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int sms = 148;
+  int rc = device_sm_count(&sms);
+  if (rc != RL_OK) return rc;
+  Layout L;
+  rc = make_layout(p, sms, &L);
+  if (rc != RL_OK) return rc;
+  if (p->B == 0) return RL_OK;
+  RL_REQUIRE(sim_floor && counts && p->Q, RL_EINVAL, "rl_maxsim_count_at_least: null pointer");
+  RL_REQUIRE(bound >= -1 && bound <= 1, RL_EINVAL, "rl_maxsim_count_at_least: bound must be -1, 0 or +1");
+  if (p->n_rows == 0) {
+    RL_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)p->B * 4, stream));
+    return RL_OK;
+  }
+  RL_REQUIRE(p->E && p->inv_norm && p->sq_norm, RL_EINVAL, "rl_maxsim_count_at_least: null index pointer");
+  RL_REQUIRE(workspace != nullptr && workspace_bytes >= L.total, RL_ENOSPACE,
+             "rl_maxsim_count_at_least: workspace %zu < required %zu", workspace_bytes, L.total);
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, RL_EINVAL, "workspace must be 256-byte aligned");
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  int32_t* cand_cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+  float* thr = reinterpret_cast<float*>(ws + L.off_thr);
+  float* eps = reinterpret_cast<float*>(ws + L.off_eps);
+  float* q_inv = reinterpret_cast<float*>(ws + L.off_qinv);
+  double* q_sq = reinterpret_cast<double*>(ws + L.off_qsq);
+  float* q_scale = reinterpret_cast<float*>(ws + L.off_qscale);
+  int32_t* ghist = reinterpret_cast<int32_t*>(ws + L.off_hist);
+  float* hist_inv_w = reinterpret_cast<float*>(ws + L.off_histw);
+  void* qimg = ws + L.off_qimg;
+
+  RL_CUDA_CHECK(cudaMemsetAsync(cand_cnt, 0, (size_t)p->B * 4, stream));
+  RL_CUDA_CHECK(cudaMemsetAsync(ghist, 0, (size_t)p->B * kHistBins * 4, stream));
+  RL_CUDA_CHECK(cudaMemsetAsync(hist_inv_w, 0, (size_t)p->B * 4, stream));
+  rc = launch_query_prep(p->Q, p->B, p->d, p->metric, L.algo, p->row_stats, q_sq, q_inv, eps, stream);
+  if (rc != RL_OK) return rc;
+  if (L.algo == RL_ALGO_TCGEN05) {
+    rc = tcgen05_prepare_queries(p, q_inv, q_scale, qimg, stream);
+    if (rc != RL_OK) return rc;
+  }
+  rc = launch_sim_floor_to_thr(sim_floor, q_sq, eps, p->metric, bound, p->B, thr, stream);
+  if (rc != RL_OK) return rc;
+
+  // One emit-mode pass over every block with a zero-capacity candidate list: rows at or above the
+  // threshold are counted, nothing is stored, and the online refinement is off (sel_count unreachable).
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.E = p->E; a.inv_norm = p->inv_norm; a.sq_norm = p->sq_norm; a.row_allowed = p->row_allowed;
+  a.Q = p->Q; a.q_inv_norm = q_inv; a.thr = thr; a.dump = nullptr; a.cand = nullptr; a.cand_cnt = cand_cnt;
+  a.n_rows = p->n_rows; a.ld = p->ld; a.n_sample_rows = 0;
+  a.d = p->d; a.B = p->B; a.metric = p->metric; a.S = 0; a.cap = 0;
+  a.ghist = ghist; a.eps = eps; a.hist_inv_w = hist_inv_w;
+  a.sel_count = 0x7fffffff;
+  a.dump_mode = 0;
+  a.n_mode_blocks = L.n_blocks;
+  rc = L.algo == RL_ALGO_TCGEN05 ? launch_scan_tcgen05(a, p, q_scale, qimg, sms, stream) : launch_scan_fp32(a, stream);
+  if (rc != RL_OK) return rc;
+  RL_CUDA_CHECK(cudaMemcpyAsync(counts, cand_cnt, (size_t)p->B * 4, cudaMemcpyDeviceToDevice, stream));
+  return RL_OK;
+}
+
 extern "C" int rl_maxsim_kernel_times(const void* workspace, float* ms) {
   RL_REQUIRE(workspace && ms, RL_EINVAL, "rl_maxsim_kernel_times: null pointer");
   std::lock_guard<std::mutex> lock(g_ev_mutex);

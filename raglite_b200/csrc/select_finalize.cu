@@ -639,6 +639,33 @@ __global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
+// ---- similarity floor -> key threshold (rl_maxsim_count_at_least) ------------------------------------
+// The scan compares approximate keys: cosine -> the similarity itself, dot -> <e,q> = sim - 1,
+// l2 -> 2<e,q> - |e|^2 = |q|^2 - dist^2 with dist = 1 - sim.  `bound` moves the threshold by the key's
+// error bound so that the count brackets the exact one (+1: no exact match is missed, -1: none is extra).
+__global__ void sim_floor_to_thr_kernel(const float* __restrict__ sim_floor, const double* __restrict__ q_sq,
+                                        const float* __restrict__ eps, int metric, int bound, int B,
+                                        float* __restrict__ thr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float f = sim_floor[b];
+  float key;
+  if (metric == RL_METRIC_COSINE) key = f;
+  else if (metric == RL_METRIC_DOT) key = f - 1.f;
+  else {
+    const double dist = 1.0 - (double)f;
+    key = dist < 0.0 ? __builtin_huge_valf() : (float)(q_sq[b] - dist * dist);
+  }
+  thr[b] = key - (float)bound * eps[b] * 1.0001f;
+}
+
+int launch_sim_floor_to_thr(const float* sim_floor, const double* q_sq, const float* eps, int metric, int bound, int B,
+                            float* thr, cudaStream_t stream) {
+  sim_floor_to_thr_kernel<<<(B + 127) / 128, 128, 0, stream>>>(sim_floor, q_sq, eps, metric, bound, B, thr);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
 int launch_query_prep(const float* Q, int B, int d, int metric, int algo, const float* row_stats, double* q_sq,
                       float* q_inv, float* eps, cudaStream_t stream) {
   query_prep_kernel<<<B, 128, 0, stream>>>(Q, B, d, metric, algo, row_stats, q_sq, q_inv, eps);

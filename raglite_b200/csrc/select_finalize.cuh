@@ -50,6 +50,8 @@ constexpr int kFinalizeScratch = 20480;  // histogram (16 KB) / flags + position
 
 int launch_query_prep(const float* Q, int B, int d, int metric, int algo, const float* row_stats, double* q_sq,
                       float* q_inv, float* eps, cudaStream_t stream);
+int launch_sim_floor_to_thr(const float* sim_floor, const double* q_sq, const float* eps, int metric, int bound, int B,
+                            float* thr, cudaStream_t stream);
 int launch_select(const SelectArgs& a, int B, cudaStream_t stream);
 int launch_finalize(const FinalizeArgs& f, int B, cudaStream_t stream);
 int launch_merge(const MergeArgs& m, cudaStream_t stream);

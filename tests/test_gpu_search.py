@@ -401,3 +401,152 @@ def test_search_and_rerank_chunk_spans_pipeline(rl):
         assert [c.index for c in s.chunks] == list(range(s.chunks[0].index, s.chunks[0].index + len(s.chunks)))
     top = rl.search_and_rerank_chunks("alpha beta gamma", num_results=4, oversample=2, config=cfg)
     assert len(top) == 4 and [len(str(c)) for c in top] == sorted((len(str(c)) for c in top), reverse=True)
+
+
+def _by_id(idx, rl, Q, k):
+    """Search ``idx`` and spell the hits as (chunk id, score) lists -- comparable across layouts."""
+    chunk, sim, count = rl.vector_search_batch(Q, num_results=k, index=idx, config=rl.RAGLiteConfig(reranker=None))
+    return [[(idx.chunk_id_of(int(c)), float(s)) for c, s in zip(chunk[b, :count[b]], sim[b, :count[b]])]
+            for b in range(len(Q))]
+
+
+@pytest.mark.parametrize("storage", ["fp32", "fp16"])
+def test_index_follows_inserts_and_deletes(rl, storage):
+    """the index tracks the chunk_embedding table as ``insert_documents`` flushes rows
+    (``_insert.py:247-255``) and ``delete_documents`` cascades (``_delete.py:146-152``).  After every
+    mutation the search must equal a search over an index built from scratch on the surviving rows,
+    and that one is checked against the oracle."""
+    d, k = 64, 7
+    parts = []
+    for f, n in enumerate((700, 450, 300)):
+        E, off = make_corpus(n, (1, 6), d, seed=90 + f, fp16_round=True)
+        owner = ovs.row_to_chunk(off)
+        parts.append((E, [f"f{f}-c{c}" for c in owner], [rl.Chunk(id=f"f{f}-c{c}", document_id=f"doc-{f}-{c // 9}", index=c % 9)
+                                                         for c in range(n)]))
+    idx = rl.CorpusIndex.from_chunk_embedding_rows(parts[0][1], parts[0][0], chunks=parts[0][2], storage=storage)
+    for E, row_ids, chunks in parts[1:]:
+        idx.append_chunk_embedding_rows(row_ids, E, chunks=chunks)
+    E_all = np.vstack([p[0] for p in parts])
+    ids_all = [i for p in parts for i in p[1]]
+    chunks_all = [c for p in parts for c in p[2]]
+    fresh = rl.CorpusIndex.from_chunk_embedding_rows(ids_all, E_all, storage=storage)
+    assert idx.n_rows == fresh.n_rows and np.array_equal(idx.chunk_off, fresh.chunk_off) and idx.max_vecs == fresh.max_vecs
+    Q = make_queries(E_all, 12, seed=95)
+    assert _by_id(idx, rl, Q, k) == _by_id(fresh, rl, Q, k)
+    with pytest.raises(ValueError):
+        idx.append_chunk_embedding_rows(["f0-c1"], E_all[:1], chunks=[rl.Chunk(id="f0-c1")])   # already present
+    with pytest.raises(ValueError):
+        idx.append_chunk_embedding_rows(["new"], E_all[:1])                                    # chunks are tracked
+
+    # deletes: by chunk id and by document (the nearest neighbours of the first queries go away)
+    doomed = {hits[0][0] for hits in _by_id(idx, rl, Q[:6], k)} | {"f1-c3", "not-there"}
+    n_del = idx.delete_chunks(sorted(doomed))
+    assert n_del == len(doomed) - 1 and idx.delete_chunks(sorted(doomed)) == 0
+    gone_docs = ["doc-2-0", "doc-0-5"]
+    n_del += idx.delete_documents(gone_docs)
+    dead = doomed | {c.id for c in chunks_all if c.document_id in gone_docs}
+    assert idx.n_live_chunks == len(chunks_all) - len(dead - {"not-there"}) == len(chunks_all) - n_del
+    keep_rows = np.array([i not in dead for i in ids_all])
+    ids_kept = [i for i in ids_all if i not in dead]
+    fresh2 = rl.CorpusIndex.from_chunk_embedding_rows(ids_kept, E_all[keep_rows], storage=storage)
+    want = _by_id(fresh2, rl, Q, k)
+    assert _by_id(idx, rl, Q, k) == want
+    for b in (0, 7):   # the rebuilt index itself against the oracle
+        ref_ids, ref_sims, _ = ovs.vector_search_sql(E_all[keep_rows], fresh2.chunk_off, Q[b], num_results=k, f64=True)
+        assert [h[0] for h in want[b]] == [fresh2.chunk_ids[c] for c in ref_ids]
+        assert np.allclose([h[1] for h in want[b]], ref_sims, atol=1e-4)
+    assert {c.id for c in idx.live_chunks} == set(ids_kept)
+
+    idx.compact(block_rows=257)   # odd block size: kept runs straddle the staging blocks
+    assert idx.n_rows == fresh2.n_rows and np.array_equal(idx.chunk_off, fresh2.chunk_off) and idx.chunk_ids == fresh2.chunk_ids
+    import torch
+    assert torch.equal(idx.E, fresh2.E) and torch.equal(idx.row_chunk, fresh2.row_chunk) and torch.equal(idx.inv_norm, fresh2.inv_norm)
+    assert _by_id(idx, rl, Q, k) == want
+
+    # a deleted document comes back with the same chunk ids (re-insert after delete)
+    back = [c for c in chunks_all if c.id in doomed]
+    rows_back = [r for r, i in enumerate(ids_all) if i in doomed]
+    idx.append_chunk_embedding_rows([ids_all[r] for r in rows_back], E_all[rows_back], chunks=back)
+    again = _by_id(idx, rl, Q[:6], k)
+    first = _by_id(fresh, rl, Q[:6], k)
+    assert [h[0][0] for h in again] == [h[0][0] for h in first]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("metric", ["cosine", "dot", "l2"])
+def test_count_at_least_brackets_the_exact_rank(rl, metric, algo):
+    """``rl_maxsim_count_at_least``: lower bound <= exact #rows with sim >= floor <= upper bound."""
+    import torch
+
+    d = 64
+    _algo_ok(rl, algo, d, metric)
+    E, off = make_corpus(900, (1, 4), d, seed=310, normalize=(metric == "cosine"))
+    Q = make_queries(E, 5, seed=311)
+    idx = rl.CorpusIndex(E, off)
+    sims = np.stack([1.0 - ovs.vector_distances_f64(E, q, metric) for q in Q])
+    floor = np.array([np.sort(s)[::-1][r] for s, r in zip(sims, (0, 9, 100, 700, len(E) - 1))], dtype=np.float32)
+    exact = (sims >= floor[:, None].astype(np.float64)).sum(1)
+    Qd, fd = torch.from_numpy(Q).cuda(), torch.from_numpy(floor).cuda()
+    ub = idx.count_at_least(Qd, fd, k=5, num_hits=40, metric=metric, algo=algo, bound=1).cpu().numpy()
+    lb = idx.count_at_least(Qd, fd, k=5, num_hits=40, metric=metric, algo=algo, bound=-1).cpu().numpy()
+    raw = idx.count_at_least(Qd, fd, k=5, num_hits=40, metric=metric, algo=algo, bound=0).cpu().numpy()
+    assert np.all(lb <= exact) and np.all(exact <= ub), (lb, exact, ub)
+    assert np.all(lb <= raw) and np.all(raw <= ub)
+    slack = 2 if algo == "fp32" else 60   # the fp16-input scan brackets within ~2.5e-3 cosine units
+    assert np.all(ub - lb <= slack + 0.1 * exact), (lb, exact, ub)
+    none = idx.count_at_least(Qd, torch.full((5,), 3.0e4 if metric == "dot" else 1.5).cuda(), k=5, num_hits=40, metric=metric, algo=algo)
+    assert int(none.sum()) == 0
+    # tombstoned rows do not count
+    idx2 = rl.CorpusIndex(E, off, chunk_ids=[str(c) for c in range(len(off) - 1)])
+    idx2.delete_chunks([str(c) for c in range(0, len(off) - 1, 2)])
+    alive_rows = np.repeat(np.arange(len(off) - 1) % 2 == 1, np.diff(off))
+    exact2 = ((sims >= floor[:, None].astype(np.float64)) & alive_rows[None]).sum(1)
+    ub2 = idx2.count_at_least(Qd, fd, k=5, num_hits=40, metric=metric, algo=algo, bound=1).cpu().numpy()
+    lb2 = idx2.count_at_least(Qd, fd, k=5, num_hits=40, metric=metric, algo=algo, bound=-1).cpu().numpy()
+    assert np.all(lb2 <= exact2) and np.all(exact2 <= ub2)
+
+
+def test_metadata_rank_then_filter_branch(rl, monkeypatch):
+    """``_search.py:96-143`` with both constants scaled down (100_000 -> 60 matching rows, 1_000_000 -> the
+    400 nearest vectors): query 0's filter keeps chunks far from it plus a few near ones, so only the
+    near ones survive the rank-first cut; for the other queries the one counting pass proves that the
+    filter-first answer stands."""
+    import raglite_b200._search as S
+
+    monkeypatch.setattr(S, "FILTER_FIRST_MAX_ROWS", 60)
+    monkeypatch.setattr(S, "RANK_FIRST_LIMIT", 400)
+    d, k = 64, 10
+    E, off = make_corpus(600, (1, 5), d, seed=320, fp16_round=True)
+    C = len(off) - 1
+    Q = make_queries(E, 3, seed=321, frac_random=0.0)
+    score0 = ovs.maxsim_scores(E, off, Q[0], "cosine", f64=True)
+    order = np.argsort(-score0)
+    tagged = np.zeros(C, dtype=bool)
+    tagged[order[C // 2:]] = True          # the far half of the corpus ...
+    tagged[order[[0, 2, 5, 30]]] = True    # ... and four chunks near query 0
+    meta = [{"topic": ["keep"] if t else ["drop"]} for t in tagged]
+    idx = rl.CorpusIndex(E, off, chunk_metadata=meta)
+    cfg = rl.RAGLiteConfig(reranker=None)
+    chunk, sim, count = rl.vector_search_batch(Q, num_results=k, metadata_filter={"topic": "keep"}, index=idx, config=cfg)
+    took_rank_first = False
+    for b in range(3):
+        got = chunk[b, :count[b]].tolist()
+        options = []
+        for lim in (400, 399, 401):   # the row sitting exactly at the cut may fall on either side
+            ids, sims, _ = ovs.vector_search_sql(E, off, Q[b], num_results=k, allowed_chunks=tagged, f64=True,
+                                                 filter_first_max=60, rank_first_limit=lim)
+            options.append((ids.tolist(), sims))
+        assert got in [o[0] for o in options], (b, got, options[0][0])
+        ref_sims = options[[o[0] for o in options].index(got)][1]
+        assert np.allclose(sim[b, :count[b]], ref_sims, atol=1e-4)
+        first_ids, _, _ = ovs.vector_search_sql(E, off, Q[b], num_results=k, allowed_chunks=tagged, f64=True)
+        took_rank_first |= got != first_ids.tolist()
+    assert took_rank_first, "query 0 must differ from the filter-first answer"
+    # few matching rows -> filter-first, whatever the corpus size
+    few = np.zeros(C, dtype=bool)
+    few[order[[1, 3, 400, 401, 402]]] = True
+    idx_few = rl.CorpusIndex(E, off, chunk_metadata=[{"topic": ["keep"] if t else ["drop"]} for t in few])
+    chunk, sim, count = rl.vector_search_batch(Q[:1], num_results=k, metadata_filter={"topic": "keep"}, index=idx_few, config=cfg)
+    ids, sims, _ = ovs.vector_search_sql(E, off, Q[0], num_results=k, allowed_chunks=few, f64=True, filter_first_max=60,
+                                         rank_first_limit=400)
+    assert chunk[0, :count[0]].tolist() == ids.tolist() and len(ids) == 5

@@ -169,3 +169,17 @@ def test_retrieve_chunk_spans_groups_and_ranks():
     assert got == [["A-5", "A-6"], ["B-2"], ["A-9"]]
     assert str(spans[0]) == "[A5][A6]" and spans[0].document_id == "A"
     assert retrieve_chunk_spans([], config=RAGLiteConfig(reranker=None)) == []
+
+
+def test_csr_from_row_chunk_ids_follows_the_table_layout():
+    """One CSR segment per run of equal chunk ids (``_insert.py:247-251``); a re-appearing id is an error."""
+    from raglite_b200._index import csr_from_row_chunk_ids
+
+    off, ids = csr_from_row_chunk_ids(["a", "a", "b", "c", "c", "c"])
+    assert off.tolist() == [0, 2, 3, 6] and ids == ["a", "b", "c"]
+    off, ids = csr_from_row_chunk_ids([])
+    assert off.tolist() == [0] and ids == []
+    with pytest.raises(ValueError):
+        csr_from_row_chunk_ids(["a", "b", "a"])
+    with pytest.raises(ValueError):
+        csr_from_row_chunk_ids(["x", "y"], known={"y"})
