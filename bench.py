@@ -298,6 +298,28 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
                 "config": {"workload": w["desc"], "pairs": total, "tokens": tok, "parallelism": f"dp{world} over queries"},
                 "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(tok * 12 // world), "d2h_bytes_per_step": int(total * 8 // world)},
                 "gpu_launches": int(86 * np.ceil(tok / world / eng.max_tokens_per_call)), "reordered": int(order.shape[0])}
+        # Tensor-pipe roofline of the whole forward (it is one fused sequence of GEMM-shaped kernels):
+        # per layer 2*T*(4H^2 + 2HF) for the linears + 4*sum(L^2)*H for QK^T and PV.
+        Hh, Ff, Ly = 384, 1536, 12
+        flops = Ly * (2.0 * tok * (4 * Hh * Hh + 2 * Hh * Ff) + 4.0 * float((lens.astype(np.float64) ** 2).sum()) * Hh)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except (OSError, ValueError):
+            pass
+        peak_tf = float(peaks.get("bf16_tflops", 1720.0))
+        ach = flops / float(dt.item()) / 1e12
+        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak_tf * world, "unit": "TFLOP/s", "frac": ach / (peak_tf * world),
+                            "traffic": None, "kernel": "whole cross-encoder forward (linear_tcgen05 + attention + LayerNorm), wall clock incl. host packing",
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops" if peaks else "fallback 1720 TFLOP/s"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import rerank as orr     # checker / CPU arm only: float32 transformers forward on a bounded sample
+            model = orr.seeded_model(seed=0)
+            n = 64
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            t1 = time.perf_counter(); orr.hf_logits(model, ids[:n], types[:n]); cdt = time.perf_counter() - t1
+            line["cpu_baseline"] = {"value": n / cdt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{n} pairs, transformers BertForSequenceClassification fp32 (oracle.rerank.hf_logits)"}
         sys.stdout.flush(); os.dup2(saved, 1); print(json.dumps(line), flush=True); os.dup2(2, 1)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

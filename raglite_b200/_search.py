@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import contextlib
 from collections.abc import Sequence
+from dataclasses import dataclass
 from typing import Any
 
 import numpy as np
@@ -205,10 +206,7 @@ def rerank_chunks(
 
 
 # ---- the steps right after the hot path ------------------------------------------
-from dataclasses import dataclass as _dataclass  # noqa: E402
-
-
-@_dataclass
+@dataclass
 class ChunkSpan:
     """A run of consecutive chunks of one document (reference ``_database.py:326-398``)."""
 

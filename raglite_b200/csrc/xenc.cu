@@ -23,15 +23,20 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kSliceK = 64;
 constexpr int kMaxN = 256;
-constexpr int kNumEpiWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kWWarp = 5;
-constexpr int kFirstLoaderWarp = 6;
+constexpr int kNumEpiWarps = 8;   // warp w reads TMEM lane quarter w % 4; warps 4..7 take the odd 32-column chunks
+constexpr int kMmaWarp = 8;
+constexpr int kWWarp = 9;
+constexpr int kFirstLoaderWarp = 10;
 constexpr int kNumLoaderWarps = 8;
+constexpr int kLoadDepth = 3;     // activation K-slices in flight per loader thread (registers)
+constexpr uint32_t kBarBytes = 256;                         // mbarriers + TMEM base pointer
+constexpr uint32_t kEpiPitch = 80;                          // bytes per staged row: 64 B of fp16 + pad (conflict-free 16 B stores)
+constexpr uint32_t kEpiWarpBytes = 32 * kEpiPitch;          // one 32 x 32 output chunk per epilogue warp
+constexpr uint32_t kEpiBytes = kNumEpiWarps * kEpiWarpBytes;
 constexpr int kThreads = (kFirstLoaderWarp + kNumLoaderWarps) * 32;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;
-constexpr uint32_t kSmemBudget = 220 * 1024;
+constexpr uint32_t kSmemBudget = 226 * 1024;
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -41,6 +46,21 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far
+// below the fp16 rounding of the stored activation): 5 FMAs, one reciprocal, one exp2.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float tail = p * t * exp2f(-1.4426950408889634f * z * z);   // 1 - erf(z), z >= 0
+  const float half_x = 0.5f * x;
+  // x >= 0: x/2 (2 - tail);  x < 0: x/2 tail
+  return x >= 0.f ? half_x * (2.f - tail) : half_x * tail;
 }
 
 // ---- weight image: W[N, K] fp32 row-major -> per (pass, k-slice) swizzled fp16 UMMA B tiles -------------
@@ -91,6 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
   uint64_t* tmem_full = empty + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  unsigned char* epi_stage = base + (size_t)t.stages * sbytes + kBarBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (t.T + kTileM - 1) / kTileM;
@@ -116,34 +137,51 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp >= kFirstLoaderWarp) {
-    // activations: fp16 rows -> swizzled K-major smem tile (UMMA A), 4 x 16-byte chunks per thread and slice
+    // activations: fp16 rows -> swizzled K-major smem tile (UMMA A), 4 x 16-byte chunks per thread and
+    // slice.  The loads of kLoadDepth slices are in flight at once (a register ring that runs across
+    // item boundaries): one memory latency per slice would otherwise bound the whole kernel.
     const int lt = threadIdx.x - kFirstLoaderWarp * 32;
     const int j = lt & 7, r0 = lt >> 3;  // chunk j of rows r0 + 32 i
+    const int64_t n_slices = my_items * t.n_ks;
+    auto issue = [&](int64_t g, uint4 (&v)[4]) {
+      if (g >= n_slices) return;
+      const int64_t it = g / t.n_ks;
+      const int ks = (int)(g - it * t.n_ks);
+      const int m_tile = (int)((first + it * stride) / t.n_pass);
+      const int col = ks * kSliceK + j * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m_tile * kTileM + r0 + 32 * i;
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < t.T && col < t.K) v[i] = __ldg(reinterpret_cast<const uint4*>(t.X + (size_t)row * t.K + col));
+      }
+    };
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t it = 0; it < my_items; ++it) {
-      const int64_t item = first + it * stride;
-      const int m_tile = (int)(item / t.n_pass);
-      for (int ks = 0; ks < t.n_ks; ++ks) {
-        uint4 v[4];
+    auto commit = [&](int64_t g, const uint4 (&v)[4]) {
+      if (g >= n_slices) return;
+      mbar_wait(&empty[stage], phase ^ 1u);
+      unsigned char* A = base + (size_t)stage * sbytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = m_tile * kTileM + r0 + 32 * i;
-          const int col = ks * kSliceK + j * 8;
-          v[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (row < t.T && col < t.K) v[i] = __ldg(reinterpret_cast<const uint4*>(t.X + (size_t)row * t.K + col));
-        }
-        mbar_wait(&empty[stage], phase ^ 1u);
-        unsigned char* A = base + (size_t)stage * sbytes;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = r0 + 32 * i;
-          *reinterpret_cast<uint4*>(A + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)) = v[i];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[stage]);
-        if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        *reinterpret_cast<uint4*>(A + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4)) = v[i];
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+    };
+    static_assert(kLoadDepth == 3, "the register ring below is written out for three slices");
+    uint4 v0[4], v1[4], v2[4];
+    issue(0, v0);
+    issue(1, v1);
+    for (int64_t g = 0; g < n_slices; g += 3) {
+      issue(g + 2, v2);
+      commit(g, v0);
+      issue(g + 3, v0);
+      commit(g + 1, v1);
+      issue(g + 4, v1);
+      commit(g + 2, v2);
     }
   } else if (warp == kWWarp) {
     if (lane == 0) {
@@ -193,50 +231,54 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       }
     }
   } else {
-    // epilogue: TMEM -> + bias -> activation -> fp16 -> global (each thread owns one token row)
-    const int q = warp;
+    // epilogue: TMEM -> + bias -> activation -> fp16 -> shared staging -> global.  A thread owns one token
+    // row of the accumulator; the two warps of a lane quarter split the 32-column chunks (even / odd).
+    // Storing straight from the row owner would issue 32 separate 16-byte requests per instruction
+    // (one per row) -- the L2 request rate, not bytes, then bounds the kernel -- so a chunk is staged in
+    // shared memory and written out with 4 lanes per row: 64 contiguous bytes per request.
+    const int q = warp & 3, half = warp >> 2;
+    unsigned char* stg = epi_stage + (size_t)warp * kEpiWarpBytes;
     for (int64_t it = 0; it < my_items; ++it) {
       const int64_t item = first + it * stride;
       const int m_tile = (int)(item / t.n_pass), pass = (int)(item % t.n_pass);
       const int nb = pass_rows(t.N, pass);
       const int n0 = pass * kMaxN;
       const int buf = (int)(it & 1);
-      const int row = m_tile * kTileM + q * 32 + lane;
+      const int row_base = m_tile * kTileM + q * 32;
       mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kMaxN);
-      auto store_chunk = [&](int c0, const uint32_t (&v)[32]) {
-        if (row < t.T) {
-          uint32_t packed[16];
+      // chunks half*32, half*32 + 64, ...  (the sibling warp on the same scheduler hides the TMEM latency)
+      for (int c0 = half * 32; c0 < nb; c0 += 64) {
+        uint32_t v[32];
+        tmem_ld32_async(taddr0 + (uint32_t)c0, v);
+        tmem_ld_wait(v);
+        const float4* b4 = reinterpret_cast<const float4*>(t.bias + n0 + c0);   // n0, c0 multiples of 32
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) {
-            float x0 = __uint_as_float(v[2 * jj]) + __ldg(t.bias + n0 + c0 + 2 * jj);
-            float x1 = __uint_as_float(v[2 * jj + 1]) + __ldg(t.bias + n0 + c0 + 2 * jj + 1);
-            if (t.act == 1) {
-              x0 = 0.5f * x0 * (1.f + erff(x0 * 0.70710678118654752f));
-              x1 = 0.5f * x1 * (1.f + erff(x1 * 0.70710678118654752f));
-            }
-            packed[jj] = pack_half2(x0, x1);
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 bb = __ldg(b4 + 2 * jj + h2);
+            const int e = 8 * jj + 4 * h2;
+            float x0 = __uint_as_float(v[e]) + bb.x, x1 = __uint_as_float(v[e + 1]) + bb.y;
+            float x2 = __uint_as_float(v[e + 2]) + bb.z, x3 = __uint_as_float(v[e + 3]) + bb.w;
+            if (t.act == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+            packed[2 * h2] = pack_half2(x0, x1);
+            packed[2 * h2 + 1] = pack_half2(x2, x3);
           }
-          uint4* dst = reinterpret_cast<uint4*>(t.Y + (size_t)row * t.N + n0 + c0);
+          *reinterpret_cast<uint4*>(stg + (uint32_t)lane * kEpiPitch + (uint32_t)jj * 16u) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncwarp();
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            dst[jj] = make_uint4(packed[4 * jj], packed[4 * jj + 1], packed[4 * jj + 2], packed[4 * jj + 3]);
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + (uint32_t)rr * kEpiPitch + (uint32_t)ch * 16u);
+          const int grow = row_base + rr;
+          if (grow < t.T) *reinterpret_cast<uint4*>(t.Y + (size_t)grow * t.N + n0 + c0 + ch * 8) = w;
         }
-      };
-      uint32_t va[32], vb[32];
-      tmem_ld32_async(taddr0, va);
-      tmem_ld_wait(va);
-      for (int c0 = 0; c0 < nb; c0 += 64) {
-        const bool has_b = c0 + 32 < nb;
-        if (has_b) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 32), vb);
-        store_chunk(c0, va);
-        if (has_b) {
-          tmem_ld_wait(vb);
-          if (c0 + 64 < nb) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 64), va);
-          store_chunk(c0 + 32, vb);
-          if (c0 + 64 < nb) tmem_ld_wait(va);
-        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -340,7 +382,24 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "r"(smem_u32(p)));
 }
 
-__global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
+// 4 x 4 transpose of 32-bit words across the four lanes of a quad: afterwards w[l] on lane c holds what
+// w[c] was on lane l.  Turns "16 contiguous bytes of a row per lane" (one 64-byte request per row) into
+// the m16n8k16 fragment layout (4-byte pieces at stride 16 bytes) and back.
+__device__ __forceinline__ void quad_transpose(uint32_t (&w)[4], int c) {
+#pragma unroll
+  for (int s = 1; s < 4; ++s) {   // selects only: a branch here would make the shuffle divergent
+    const int p = c ^ s;
+    const uint32_t lo = (p & 1) ? w[1] : w[0], hi = (p & 1) ? w[3] : w[2];
+    const uint32_t got = __shfl_xor_sync(0xffffffffu, (p & 2) ? hi : lo, s);
+    w[0] = p == 0 ? got : w[0];
+    w[1] = p == 1 ? got : w[1];
+    w[2] = p == 2 ? got : w[2];
+    w[3] = p == 3 ? got : w[3];
+  }
+}
+
+template <bool QUAD>   // QUAD: 16-byte Q loads / context stores through a quad transpose; else (default) 4-byte fragment pieces
+__global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                         int H, int n_heads, float scale_log2e, __half* __restrict__ ctx) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   const int seq = blockIdx.x, head = blockIdx.y;
@@ -350,6 +409,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   __half* Vs = Ks + (size_t)Lp * kAttPitch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t ld = (size_t)3 * H;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
     const int j = idx >> 2, c = idx & 3;
     uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
@@ -363,18 +423,50 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
   }
   __syncthreads();
   const int r = lane >> 2, cp = (lane & 3) * 2;
+  // Q fragments (A operand of S = Q K^T) of a 16-query block; the next block's are fetched while this
+  // one is computed.
+  const int qc = lane & 3;
+  auto load_q = [&](int qb, uint32_t (&a)[2][4]) {   // raw 16-byte row chunks; finish_q turns them into fragments
+    const int q0 = qb * 16 + r, q1 = q0 + 8;
+    if (!QUAD) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const __half* p0 = qkv + (size_t)(t0 + q0) * ld + head * 32 + ks * 16 + cp;
+        const __half* p1 = qkv + (size_t)(t0 + q1) * ld + head * 32 + ks * 16 + cp;
+        a[ks][0] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0)) : 0u;
+        a[ks][1] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1)) : 0u;
+        a[ks][2] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0 + 8)) : 0u;
+        a[ks][3] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1 + 8)) : 0u;
+      }
+      return;
+    }
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 u0 = q0 < L ? __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + q0) * ld + head * 32 + qc * 8)) : z;
+    const uint4 u1 = q1 < L ? __ldg(reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + q1) * ld + head * 32 + qc * 8)) : z;
+    a[0][0] = u0.x; a[0][1] = u0.y; a[0][2] = u0.z; a[0][3] = u0.w;
+    a[1][0] = u1.x; a[1][1] = u1.y; a[1][2] = u1.z; a[1][3] = u1.w;
+  };
+  auto finish_q = [&](const uint32_t (&raw)[2][4], uint32_t (&a)[2][4]) {
+    if (!QUAD) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[ks][e] = raw[ks][e];
+      return;
+    }
+    uint32_t w0[4] = {raw[0][0], raw[0][1], raw[0][2], raw[0][3]};
+    uint32_t w1[4] = {raw[1][0], raw[1][1], raw[1][2], raw[1][3]};
+    quad_transpose(w0, qc);   // w0[l] = row q0, columns l*8 + cp, +1
+    quad_transpose(w1, qc);
+    a[0][0] = w0[0]; a[0][2] = w0[1]; a[1][0] = w0[2]; a[1][2] = w0[3];
+    a[0][1] = w1[0]; a[0][3] = w1[1]; a[1][1] = w1[2]; a[1][3] = w1[3];
+  };
+  uint32_t a[2][4], a_next[2][4];
+  load_q(warp, a_next);   // rows >= L read as zero, so a block past the end is harmless
   for (int qb = warp; qb * 16 < L; qb += 4) {
     const int q0 = qb * 16 + r, q1 = q0 + 8;
-    uint32_t a[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const __half* p0 = qkv + (size_t)(t0 + q0) * ld + head * 32 + ks * 16 + cp;
-      const __half* p1 = qkv + (size_t)(t0 + q1) * ld + head * 32 + ks * 16 + cp;
-      a[ks][0] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0)) : 0u;
-      a[ks][1] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1)) : 0u;
-      a[ks][2] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0 + 8)) : 0u;
-      a[ks][3] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1 + 8)) : 0u;
-    }
+    finish_q(a_next, a);
+    load_q(qb + 4, a_next);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float O[4][4];
 #pragma unroll
@@ -393,12 +485,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
         mma16816(S[j], a[1], b[2], b[3]);
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      const bool ragged = kb + 64 > L;   // only the last key block holds padding keys
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int key = kb + j * 8 + cp + (e & 1);
-          const float v = key < L ? S[j][e] * scale_log2e : -INFINITY;
+          float v = S[j][e] * scale_log2e;
+          if (ragged && kb + j * 8 + cp + (e & 1) >= L) v = -INFINITY;
           S[j][e] = v;
           if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
         }
@@ -442,13 +535,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const __half* __restrict
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    uint32_t o0[4], o1[4];
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) {
-      if (q0 < L)
-        *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q0) * H + head * 32 + dn * 8 + cp) = pack_half2(O[dn][0] * inv0, O[dn][1] * inv0);
-      if (q1 < L)
-        *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q1) * H + head * 32 + dn * 8 + cp) = pack_half2(O[dn][2] * inv1, O[dn][3] * inv1);
+      o0[dn] = pack_half2(O[dn][0] * inv0, O[dn][1] * inv0);
+      o1[dn] = pack_half2(O[dn][2] * inv1, O[dn][3] * inv1);
     }
+    if (!QUAD) {
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        if (q0 < L) *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q0) * H + head * 32 + dn * 8 + cp) = o0[dn];
+        if (q1 < L) *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q1) * H + head * 32 + dn * 8 + cp) = o1[dn];
+      }
+      continue;
+    }
+    quad_transpose(o0, qc);   // lane qc now holds columns qc*8 .. qc*8+7 of its rows: one 16-byte store each
+    quad_transpose(o1, qc);
+    if (q0 < L)
+      *reinterpret_cast<uint4*>(ctx + (size_t)(t0 + q0) * H + head * 32 + qc * 8) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+    if (q1 < L)
+      *reinterpret_cast<uint4*>(ctx + (size_t)(t0 + q1) * H + head * 32 + qc * 8) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
   }
 }
 
@@ -505,7 +611,8 @@ static int launch_linear(const __half* X, const void* img, const float* bias, __
   t.X = X; t.img = reinterpret_cast<const __half*>(img); t.bias = bias; t.Y = Y; t.T = T; t.N = N; t.K = K; t.act = act;
   t.n_pass = (N + kMaxN - 1) / kMaxN;
   t.n_ks = (K + kSliceK - 1) / kSliceK;
-  const uint32_t tail = (2 * kMaxStages + 4) * 8 + 64;
+  static_assert((2 * kMaxStages + 4) * 8 + 8 <= kBarBytes, "barrier block overflows its slot");
+  const uint32_t tail = kBarBytes + kEpiBytes;
   int stages = (int)((kSmemBudget - 1024 - tail) / lin_stage_bytes());
   if (stages > kMaxStages) stages = kMaxStages;
   t.stages = stages;
@@ -522,6 +629,7 @@ extern "C" int rl_xenc_linear(const void* X, const void* image, const float* bia
                               void* stream) {
   RL_REQUIRE(X && image && bias && Y && T >= 0, RL_EINVAL, "rl_xenc_linear: bad arguments");
   RL_REQUIRE(N % 32 == 0 && K % 8 == 0, RL_EUNSUPPORTED, "rl_xenc_linear: N %% 32 and K %% 8 must be 0");
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, RL_EINVAL, "rl_xenc_linear: bias must be 16-byte aligned");
   if (T == 0) return RL_OK;
   int dev = 0, sms = 148;
   RL_CUDA_CHECK(cudaGetDevice(&dev));
@@ -565,13 +673,19 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   RL_CUDA_CHECK(cudaGetLastError());
   const size_t att_smem = (size_t)((max_len + 63) / 64 * 64) * kAttPitch * 2 * sizeof(__half);
   RL_REQUIRE(att_smem <= 200 * 1024, RL_EUNSUPPORTED, "rl_xenc_score: max_len=%d too long for the attention kernel", max_len);
-  RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  // A/B switch for the Q loads / context stores.  Measured back to back on one B200 (262 k tokens per
+  // layer): 4-byte fragment pieces 0.744 ms, 16-byte rows + quad transpose 1.100 ms -- so pieces are
+  // the default and RL_XENC_ATT_QUAD=1 selects the transpose variant.
+  static const bool att_quad = []() { const char* e = getenv("RL_XENC_ATT_QUAD"); return e ? atoi(e) != 0 : false; }();
+  RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   const float scale = 1.4426950408889634f / sqrtf(32.f);  // softmax in the exp2 domain
   for (int l = 0; l < w->n_layers; ++l) {
     const rl_xenc_layer& L = w->layers[l];
     int rc = launch_linear(hidden, L.qkv_img, L.qkv_bias, qkv, T, 3 * H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
-    attention_kernel<<<dim3(P, nh), 128, att_smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
+    if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, att_smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
+    else attention_kernel<false><<<dim3(P, nh), 128, att_smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
     RL_CUDA_CHECK(cudaGetLastError());
     rc = launch_linear(ctx, L.o_img, L.o_bias, tmp, T, H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
