@@ -17,8 +17,9 @@ import torch.multiprocessing as mp
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def shard_hits_numpy(E, off, Q, lo, hi, num_hits):
-    """Per-shard output of rl_maxsim_topk restated in NumPy: top-num_hits vectors (sim, global chunk)."""
+def shard_hits_numpy(E, off, Q, lo, hi, num_hits, allowed_chunks=None):
+    """Per-shard output of rl_maxsim_topk restated in NumPy: top-num_hits vectors (sim, global chunk);
+    ``allowed_chunks`` (bool per global chunk) restates the ``row_allowed`` mask."""
     from oracle import vector_search as ovs
 
     r0, r1 = int(off[lo]), int(off[hi])
@@ -30,7 +31,8 @@ def shard_hits_numpy(E, off, Q, lo, hi, num_hits):
     count = np.zeros(B, np.int32)
     for b, q in enumerate(Q):
         dist_ = ovs.vector_distances_f64(Es, q, "cosine")
-        order = np.argsort(dist_, kind="stable")[:num_hits]
+        rows = np.arange(len(dist_)) if allowed_chunks is None else np.nonzero(np.asarray(allowed_chunks)[r2c])[0]
+        order = rows[np.argsort(dist_[rows], kind="stable")][:num_hits]
         n = len(order)
         sim[b, :n] = (1.0 - dist_[order]).astype(np.float32)
         chunk[b, :n] = r2c[order]
@@ -81,6 +83,41 @@ def _worker(rank: int, world: int, port: int, tmp: str) -> None:
         ref_ids, ref_sims, _ = ovs.vector_search_sql(E, off, q, num_results=k, f64=True)
         assert merged[b][0].tolist() == ref_ids.tolist()
         assert np.allclose(merged[b][1], ref_sims, atol=1e-6)
+    # Rank-then-filter metadata branch on a sharded corpus (_search.py:122-143): the counts of the rank
+    # probe are all-reduced, the cut is found by bisection, every rank truncates the gathered lists alike.
+    from raglite_b200._dist import ShardedIndex
+    from raglite_b200._index import limit_hits_to_nearest
+
+    class FakeShard:   # the local CorpusIndex, restated on the host: exact float64 similarities
+        storage, stats = "fp32", torch.tensor([1.0, 1.0, 1.0, 0.0])
+
+        def count_at_least(self, Qd, floor, **_):
+            r0, r1 = int(off[lo]), int(off[hi])
+            sims = [1.0 - ovs.vector_distances_f64(E[r0:r1], q, "cosine") for q in Qd.numpy()]
+            return torch.tensor([int((s >= float(f)).sum()) for s, f in zip(sims, floor)], dtype=torch.int32)
+
+    limit = 300
+    score0 = ovs.maxsim_scores(E, off, Q[0], "cosine", f64=True)
+    order0 = np.argsort(-score0)
+    tagged = np.zeros(len(off) - 1, dtype=bool)
+    tagged[order0[len(order0) // 2:]] = True       # far from query 0 ...
+    tagged[order0[[0, 3, 7]]] = True               # ... plus three near chunks
+    sim, chunk, count = shard_hits_numpy(E, off, Q, lo, hi, num_hits, allowed_chunks=tagged)
+    g_sim, g_chunk, g_count = gather_hits(torch.from_numpy(sim), torch.from_numpy(chunk), torch.from_numpy(count),
+                                          dist.group.WORLD)
+    sharded = ShardedIndex(FakeShard(), dist.group.WORLD)
+    kept = limit_hits_to_nearest(sharded, torch.from_numpy(Q), g_sim, g_count, k=k, num_hits=num_hits, metric="cosine",
+                                 limit=limit)
+    merged = merge_numpy(g_sim.numpy(), g_chunk.numpy(), kept.numpy(), num_hits, k)
+    changed = 0
+    for b, q in enumerate(Q):
+        ref_ids, ref_sims, _ = ovs.vector_search_sql(E, off, q, num_results=k, allowed_chunks=tagged, f64=True,
+                                                     filter_first_max=0, rank_first_limit=limit)
+        assert merged[b][0].tolist() == ref_ids.tolist(), (b, merged[b][0], ref_ids)
+        assert np.allclose(merged[b][1], ref_sims, atol=1e-6)
+        first_ids, _, _ = ovs.vector_search_sql(E, off, q, num_results=k, allowed_chunks=tagged, f64=True)
+        changed += ref_ids.tolist() != first_ids.tolist()
+    assert changed >= 1, "the cut must change at least query 0's answer"
     dist.barrier()
     dist.destroy_process_group()
     Path(tmp, f"ok{rank}").write_text("ok")
