@@ -387,6 +387,12 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "r"(smem_u32(p)));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // 4 x 4 transpose of 32-bit words across the four lanes of a quad: afterwards w[l] on lane c holds what
 // w[c] was on lane l.  Turns "16 contiguous bytes of a row per lane" (one 64-byte request per row) into
 // the m16n8k16 fragment layout (4-byte pieces at stride 16 bytes) and back.
@@ -489,23 +495,29 @@ __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restr
         mma16816(S[j], a[0], b[0], b[1]);
         mma16816(S[j], a[1], b[2], b[3]);
       }
+      // Online softmax in the exp2 domain.  The running maxima are kept scaled (m = max(S) * scale);
+      // the scale itself is folded into the exponent's FMA, so a score costs one FMNMX, one FFMA, one
+      // ex2 and one FADD.  Only the last key block holds padding keys.
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      const bool ragged = kb + 64 > L;   // only the last key block holds padding keys
+      if (kb + 64 > L) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = S[j][e] * scale_log2e;
-          if (ragged && kb + j * 8 + cp + (e & 1) >= L) v = -INFINITY;
-          S[j][e] = v;
-          if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
-        }
+          for (int e = 0; e < 4; ++e)
+            if (kb + j * 8 + cp + (e & 1) >= L) S[j][e] = -INFINITY;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(S[j][0], S[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(S[j][2], S[j][3]));
+      }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every key block holds a valid key
-      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      // finite: every key block holds a valid key (scale > 0, so max commutes with the scaling)
+      const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);
+      const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
       l0 *= c0; l1 *= c1;
 #pragma unroll
       for (int i = 0; i < 4; ++i) { O[i][0] *= c0; O[i][1] *= c0; O[i][2] *= c1; O[i][3] *= c1; }
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restr
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pexp = exp2f(S[j][e] - (e < 2 ? mn0 : mn1));
+          const float pexp = ex2_approx(fmaf(S[j][e], scale_log2e, e < 2 ? -mn0 : -mn1));   // -inf -> 0
           S[j][e] = pexp;
           if (e < 2) l0 += pexp; else l1 += pexp;
         }
