@@ -59,7 +59,8 @@ int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes
 /* ---- Index build -------------------------------------------------------------------------
  * Per-row statistics of the embedding matrix E[n_rows, d] (row stride ld floats): inv_norm[j] =
  * 1/|e_j| (0 for a zero row), sq_norm[j] = |e_j|^2, and four global statistics used to scale rows for
- * the fp16 scan (stats[4], device floats, must be zeroed by the caller): [0] max row norm, [1] max
+ * the fp16 scan (stats[4], device floats, zeroed by the caller once -- the kernel folds maxima in, so
+ * appended rows (insert_documents flushes, _insert.py:247-255) only need a call over the new rows): [0] max row norm, [1] max
  * |element|, [2] max 1/|e_j| over non-zero rows, [3] 1 if any row is all-zero.  Replaces nothing in the reference (DuckDB recomputes norms per query inside
  * array_cosine_distance); it is the device-side part of building the resident index from the
  * chunk_embedding table (_database.py:403-430). */
@@ -86,7 +87,8 @@ int rl_adapter_apply(const double* A, const float* Q_in, float* Q_out, int B, in
  *   E[n_rows,d] float32 row-major (ld = row stride in floats), inv_norm/sq_norm from
  *   rl_row_stats, row_chunk from rl_chunk_row_map, chunk_base = global index of this shard's
  *   first chunk, max_vecs_per_chunk = max CSR segment length, row_stats = stats from rl_row_stats.
- *   row_allowed: optional uint8[n_rows] (metadata filter-first branch, _search.py:105-121), or NULL.
+ *   row_allowed: optional uint8[n_rows], or NULL: rows with a zero byte do not take part -- the metadata
+ *     filter (_search.py:82-121) and the tombstones of deleted chunks (_delete.py:146-152), ANDed by the caller.
  *   Q[B,d] float32 (already adapter-applied).
  *   num_hits > 0: reference SQL semantics -- the num_hits vectors with smallest distance
  *     (_search.py:75-79); hits are those vectors, ascending distance.
@@ -218,7 +220,8 @@ typedef struct rl_xenc_weights {
 size_t rl_xenc_linear_image_bytes(int N, int K);
 /* W[N, K] float32 row-major (torch nn.Linear.weight) -> packed fp16 image. */
 int rl_xenc_pack_linear(const float* W, int N, int K, void* image, void* stream);
-/* Y[T, N] (fp16) = act(X[T, K] (fp16) W^T + bias); act 0 = identity, 1 = GELU(erf). */
+/* Y[T, N] (fp16) = act(X[T, K] (fp16) W^T + bias); act 0 = identity, 1 = GELU(erf).  N % 32 == 0,
+ * K % 8 == 0, bias 16-byte aligned. */
 int rl_xenc_linear(const void* X, const void* image, const float* bias, void* Y, int T, int N, int K, int act,
                    void* stream);
 size_t rl_xenc_workspace_bytes(const rl_xenc_weights* w, int T);
