@@ -31,7 +31,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_METRIC, RL_STATUS_CAND_OVERFLOW, ScanParams, ScanStats, check
+from ._lib import (RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_MAX_SURVIVORS, RL_METRIC, RL_STATUS_CAND_OVERFLOW,
+                   RL_STATUS_TIE_OVERFLOW, ScanParams, ScanStats, check)
 from ._typing import ChunkId
 
 
@@ -518,14 +519,37 @@ class CorpusIndex:
         return dict(zip(("prep", "sample_scan", "select", "main_scan", "finalize"), (float(x) for x in ms), strict=True))
 
     def scan_checked(self, Q: torch.Tensor, **kw: Any) -> ScanResult:
-        """Scan, read the status back, and re-run with tightened thresholds while any query's
-        candidate list overflowed (rare: adversarial corpus order)."""
-        res = self.scan(Q, **kw)
+        """Scan, read the status back and resolve what the single pass could not:
+
+        * candidate-list overflow (adversarial corpus order): re-run with the tightened thresholds the
+          first pass left in the workspace, up to four times;
+        * more than ``RL_MAX_SURVIVORS`` vectors inside the coarse scan's error band of the cut (dense
+          low-dimensional data, thousands of near-duplicates): re-run those queries with the float32
+          scan, whose band is an order of magnitude narrower.
+
+        Anything still unresolved raises -- a silently truncated survivor list could drop a true hit."""
+        kw = dict(kw)
+        out = kw.pop("out", None)
+        res = self.scan(Q, **kw, out=out)
+        status = res.status.cpu()
         for _ in range(4):
-            status = res.status.cpu()
             if not bool((status & RL_STATUS_CAND_OVERFLOW).any()):
                 break
             res = self.scan(Q, **{**kw, "flags": kw.get("flags", 0) | RL_FLAG_REUSE_THRESHOLDS}, out=res)
+            status = res.status.cpu()
+        if bool((status & RL_STATUS_CAND_OVERFLOW).any()):
+            raise _lib.RagliteB200Error("candidate lists still overflow after four threshold refinements; pass a larger cand_cap")
+        tie = (status & RL_STATUS_TIE_OVERFLOW) != 0
+        if bool(tie.any()):
+            if self.storage != "fp32" or kw.get("algo", "auto") == "fp32":
+                raise _lib.RagliteB200Error(
+                    f"{int(tie.sum())} queries have more than {RL_MAX_SURVIVORS} vectors within the scan's error band of "
+                    "the cut (massive ties): the ranking cannot be resolved")
+            rows = torch.nonzero(tie).flatten().to(self.device)
+            sub = self.scan_checked(Q[rows].contiguous(),
+                                    **{**kw, "algo": "fp32", "flags": kw.get("flags", 0) & ~RL_FLAG_REUSE_THRESHOLDS})
+            res.hit_sim[rows], res.hit_chunk[rows] = sub.hit_sim, sub.hit_chunk
+            res.hit_count[rows], res.status[rows] = sub.hit_count, sub.status
         return res
 
     def chunk_id_of(self, global_chunk: int) -> ChunkId:

@@ -18,6 +18,7 @@ RL_FLAG_REUSE_THRESHOLDS = 1
 RL_FLAG_TIME_KERNELS = 2
 RL_STATUS_CAND_OVERFLOW = 1
 RL_STATUS_TIE_OVERFLOW = 2
+RL_MAX_SURVIVORS = 4096   # finalize window (include/raglite_b200.h)
 RL_MAX_SURVIVORS = 4096
 
 EXPORTS = [

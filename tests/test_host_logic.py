@@ -183,3 +183,54 @@ def test_csr_from_row_chunk_ids_follows_the_table_layout():
         csr_from_row_chunk_ids(["a", "b", "a"])
     with pytest.raises(ValueError):
         csr_from_row_chunk_ids(["x", "y"], known={"y"})
+
+
+def test_scan_checked_resolves_or_raises():
+    """Host control flow around the status bits: threshold-refinement retries, float32 re-scan of the
+    queries whose survivor window overflowed, and loud failure for whatever stays unresolved."""
+    import torch
+
+    from raglite_b200 import _lib
+    from raglite_b200._index import CorpusIndex, ScanResult
+
+    def fake_index(script):
+        idx = object.__new__(CorpusIndex)
+        idx.storage, idx.device, idx.calls = "fp32", torch.device("cpu"), []
+
+        def scan(Q, *, out=None, **kw):
+            idx.calls.append((int(Q.shape[0]), kw.get("algo", "auto"), kw.get("flags", 0)))
+            status = torch.tensor(script(len(idx.calls), int(Q.shape[0]), kw), dtype=torch.int32)
+            B = int(Q.shape[0])
+            tag = float(len(idx.calls))
+            return ScanResult(torch.full((B, 2), tag), torch.full((B, 2), int(tag), dtype=torch.int64),
+                              torch.full((B,), 2, dtype=torch.int32), status, 2, 1)
+
+        idx.scan = scan
+        return idx
+
+    Q = torch.zeros((3, 4))
+    # clean first pass
+    idx = fake_index(lambda n, B, kw: [0] * B)
+    assert idx.scan_checked(Q, k=1, num_hits=2).hit_sim[0, 0] == 1.0 and len(idx.calls) == 1
+    # candidate overflow twice, then clean: retries reuse the thresholds
+    idx = fake_index(lambda n, B, kw: [1, 0, 0] if n < 3 else [0] * B)
+    idx.scan_checked(Q, k=1, num_hits=2)
+    assert [c[2] for c in idx.calls] == [0, _lib.RL_FLAG_REUSE_THRESHOLDS, _lib.RL_FLAG_REUSE_THRESHOLDS]
+    # candidate overflow that never clears -> error
+    idx = fake_index(lambda n, B, kw: [1] * B)
+    with pytest.raises(_lib.RagliteB200Error):
+        idx.scan_checked(Q, k=1, num_hits=2)
+    assert len(idx.calls) == 5
+    # survivor-window overflow on query 1: that query alone is re-scanned with the float32 kernel
+    idx = fake_index(lambda n, B, kw: [0, 2, 0] if kw.get("algo", "auto") != "fp32" else [0] * B)
+    res = idx.scan_checked(Q, k=1, num_hits=2, algo="tcgen05")
+    assert idx.calls == [(3, "tcgen05", 0), (1, "fp32", 0)]
+    assert res.hit_sim[:, 0].tolist() == [1.0, 2.0, 1.0] and res.status.tolist() == [0, 0, 0]
+    # ... and if the float32 scan cannot resolve it either, or the storage is fp16 -> error
+    idx = fake_index(lambda n, B, kw: [2] * B)
+    with pytest.raises(_lib.RagliteB200Error):
+        idx.scan_checked(Q, k=1, num_hits=2)
+    idx = fake_index(lambda n, B, kw: [0, 2, 0])
+    idx.storage = "fp16"
+    with pytest.raises(_lib.RagliteB200Error):
+        idx.scan_checked(Q, k=1, num_hits=2)
