@@ -103,7 +103,17 @@ struct LinArgs {
   __half* Y;           // [T, N]
   int T, N, K, act;    // act: 0 none, 1 GELU(erf)
   int n_pass, n_ks, stages;
+  int cp_async;        // 1: activation tile through cp.async (no register staging; every free stage in flight)
 };
+
+// 16-byte asynchronous global -> shared copy (zero-fills when src_bytes == 0) and the mbarrier arrive
+// that fires once all of this thread's earlier cp.async have landed.
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 __host__ __device__ inline uint32_t lin_stage_bytes() { return kABytes + kMaxN * 128u; }
 
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < t.stages; ++i) {
-      mbar_init(&full[i], kNumLoaderWarps + 1);
+      mbar_init(&full[i], (t.cp_async ? kNumLoaderWarps * 32 : kNumLoaderWarps) + 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -176,6 +186,29 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       if (lane == 0) mbar_arrive(&full[stage]);
       if (++stage == t.stages) { stage = 0; phase ^= 1u; }
     };
+    if (t.cp_async) {
+      // Experimental (RL_XENC_CPASYNC=1): each thread fires its four 16-byte copies straight into the
+      // swizzled tile and lets the hardware arrive on the stage's barrier when they land, so the
+      // loaders run ahead by as many stages as are free instead of by the depth of a register ring.
+      for (int64_t g = 0; g < n_slices; ++g) {
+        const int64_t it = g / t.n_ks;
+        const int ks = (int)(g - it * t.n_ks);
+        const int m_tile = (int)((first + it * stride) / t.n_pass);
+        const int col = ks * kSliceK + j * 8;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const uint32_t A = smem_u32(base + (size_t)stage * sbytes);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 32 * i;
+          const int row = m_tile * kTileM + r;
+          const bool ok = row < t.T && col < t.K;
+          cp_async_16(A + (uint32_t)r * 128u + (((uint32_t)j ^ ((uint32_t)r & 7u)) << 4),
+                      ok ? t.X + (size_t)row * t.K + col : t.X, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(&full[stage]);
+        if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+      }
+    } else {
     static_assert(kLoadDepth == 3, "the register ring below is written out for three slices");
     uint4 v0[4], v1[4], v2[4];
     issue(0, v0);
@@ -187,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       commit(g + 1, v1);
       issue(g + 4, v1);
       commit(g + 2, v2);
+    }
     }
   } else if (warp == kWWarp) {
     if (lane == 0) {
@@ -628,6 +662,8 @@ static int launch_linear(const __half* X, const void* img, const float* bias, __
   t.X = X; t.img = reinterpret_cast<const __half*>(img); t.bias = bias; t.Y = Y; t.T = T; t.N = N; t.K = K; t.act = act;
   t.n_pass = (N + kMaxN - 1) / kMaxN;
   t.n_ks = (K + kSliceK - 1) / kSliceK;
+  const char* cpa = getenv("RL_XENC_CPASYNC");   // read per launch: tools/time_linear.py A/Bs it in one process
+  t.cp_async = (cpa != nullptr && atoi(cpa) != 0) ? 1 : 0;
   static_assert((2 * kMaxStages + 4) * 8 + 8 <= kBarBytes, "barrier block overflows its slot");
   const uint32_t tail = kBarBytes + kEpiBytes;
   int stages = (int)((kSmemBudget - 1024 - tail) / lin_stage_bytes());
