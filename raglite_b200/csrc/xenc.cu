@@ -209,18 +209,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
         if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     } else {
-    static_assert(kLoadDepth == 3, "the register ring below is written out for three slices");
-    uint4 v0[4], v1[4], v2[4];
-    issue(0, v0);
-    issue(1, v1);
-    for (int64_t g = 0; g < n_slices; g += 3) {
-      issue(g + 2, v2);
-      commit(g, v0);
-      issue(g + 3, v0);
-      commit(g + 1, v1);
-      issue(g + 4, v1);
-      commit(g + 2, v2);
-    }
+      static_assert(kLoadDepth == 3, "the register ring below is written out for three slices");
+      uint4 v0[4], v1[4], v2[4];
+      issue(0, v0);
+      issue(1, v1);
+      for (int64_t g = 0; g < n_slices; g += 3) {
+        issue(g + 2, v2);
+        commit(g, v0);
+        issue(g + 3, v0);
+        commit(g + 1, v1);
+        issue(g + 4, v1);
+        commit(g + 2, v2);
+      }
     }
   } else if (warp == kWWarp) {
     if (lane == 0) {
