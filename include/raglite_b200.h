@@ -46,7 +46,8 @@ extern "C" {
 
 /* Per-query status bits written by rl_maxsim_topk. */
 #define RL_STATUS_CAND_OVERFLOW 1 /* candidate list overflowed: call again with REUSE_THRESHOLDS */
-#define RL_STATUS_TIE_OVERFLOW 2  /* > RL_MAX_SURVIVORS rows within the error band of the cut   */
+#define RL_STATUS_TIE_OVERFLOW 2  /* reserved (never set since v101: more than RL_MAX_SURVIVORS rows inside the error
+                                     band of the cut are rescored by a streaming pass over the candidate list) */
 
 #define RL_MAX_SURVIVORS 4096
 
@@ -73,6 +74,13 @@ int rl_row_stats_f16(const void* E, int64_t n_rows, int d, int64_t ld, float* in
 /* row_chunk[j] = c for chunk_off[c] <= j < chunk_off[c+1]  (CSR -> per-row owner; the
  * chunk_embedding.chunk_id column, _database.py:421). */
 int rl_chunk_row_map(const int64_t* chunk_off, int64_t n_chunks, int32_t* row_chunk, void* stream);
+
+/* Per-row byte mask for rl_scan_params.row_allowed: out[j] = chunk_ok[row_chunk[j]] AND alive[j].
+ * chunk_ok (uint8 [n_chunks], or NULL = every chunk) is the metadata filter resolved per chunk (the JSON
+ * containment tests of _search.py:82-95), alive (uint8 [n_rows], or NULL) the tombstones of deleted
+ * chunks (_delete.py:146-152).  row_chunk, alive and out must be 16-byte aligned. */
+int rl_row_mask(const uint8_t* chunk_ok, const int32_t* row_chunk, const uint8_t* alive, int64_t n_rows,
+                uint8_t* out, void* stream);
 
 /* ---- Query adapter apply: _search.py:58-62 -------------------------------------------------
  * Q_out[b,:] = round_to(A @ Q_in[b,:]) with A[d,d] float64 row-major exactly as the reference
@@ -156,6 +164,10 @@ int rl_maxsim_count_at_least(const rl_scan_params* p, const float* sim_floor, in
  * ms[4] = finalize.  CUDA events are recorded on the launching stream; the call synchronises on the
  * last one.  Diagnostics for bench.py's roofline figure. */
 int rl_maxsim_kernel_times(const void* workspace, float* ms);
+
+/* Releases the timing events tied to a workspace pointer (created on the first RL_FLAG_TIME_KERNELS call);
+ * call before freeing the workspace.  No-op for a workspace that was never timed. */
+int rl_maxsim_release(const void* workspace);
 
 /* Debug/test hook: copy the sampled approximate keys of the last call (float32 [B, n_sample_rows],
  * sample position p <-> row (p / 128) * sample_stride * 128 + p % 128) into dst (device memory);

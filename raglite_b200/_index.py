@@ -31,8 +31,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_MAX_SURVIVORS, RL_METRIC, RL_STATUS_CAND_OVERFLOW,
-                   RL_STATUS_TIE_OVERFLOW, ScanParams, ScanStats, check)
+from ._lib import RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_METRIC, RL_STATUS_CAND_OVERFLOW, ScanParams, ScanStats, check
 from ._typing import ChunkId
 
 
@@ -153,14 +152,25 @@ class CorpusIndex:
         self.chunks = list(chunks) if chunks is not None else None
         self.chunk_metadata = list(chunk_metadata) if chunk_metadata is not None else None
         self._alive: torch.Tensor | None = None        # uint8 [n_rows]; None = no tombstones
+        self._alive_buf: torch.Tensor | None = None    # capacity buffer behind _alive
         self._bufs: dict[str, torch.Tensor] | None = None  # owned capacity buffers once the index has grown
         self._chunk_alive = np.ones(self.n_chunks, dtype=bool)
         self._chunk_pos: dict[ChunkId, int] | None = None
         self.query_adapter: np.ndarray | None = None  # IndexMetadata["default"]["query_adapter"]
         self._adapter_dev: torch.Tensor | None = None
-        self._ws: torch.Tensor | None = None
-        self._lock = threading.Lock()
+        # One workspace per CUDA stream: a scan is asynchronous, so two host threads driving two streams
+        # must never share the thresholds / candidate lists a retry reads back (reference callers search
+        # from thread pools, _rag.py:317).  The lock is re-entrant: scan_checked / search_to_host hold it
+        # across the status read-back and the retries.
+        self._ws: dict[int, torch.Tensor] = {}
+        self._lock = threading.RLock()
+        self._shard_guard: Any | None = None           # the ShardedIndex this shard belongs to, if any
+        self._meta_inv: dict[tuple[str, Any], np.ndarray] | None = None   # (key, value) -> chunk indices
+        self._meta_inv_chunks = 0                      # chunks covered by _meta_inv
+        self._filter_cache: dict[Any, tuple[torch.Tensor, int]] = {}      # filter -> (chunk_ok uint8 [C], matching live rows)
+        self._pinned: dict[int, torch.Tensor] = {}     # result staging buffers (pinned host memory) by size
         self.last_params: ScanParams | None = None
+        self.last_ws: torch.Tensor | None = None
         with torch.cuda.device(self.device):
             self.inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
             self.sq_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
@@ -283,7 +293,10 @@ class CorpusIndex:
                     raise ValueError(f"chunk_id {cid!r} is already in the index")
         if m == 0:
             return
+        if self._shard_guard is not None:
+            self._shard_guard.check_local_growth(self.n_chunks + c_new)
         with self._lock, torch.cuda.device(self.device):
+            self._invalidate_filters()
             rows = self._to_storage(E)
             n0 = self.n_rows
             self._reserve(n0 + m)
@@ -346,6 +359,7 @@ class CorpusIndex:
         lo, hi = self.chunk_off[local], self.chunk_off[local + 1]
         rows = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in zip(lo, hi, strict=True)]) if len(local) else lo
         with self._lock, torch.cuda.device(self.device):
+            self._invalidate_filters()
             if self._alive is None:
                 self._alive = torch.ones(self.n_rows, dtype=torch.uint8, device=self.device)
             if len(rows):
@@ -356,10 +370,14 @@ class CorpusIndex:
     def compact(self, block_rows: int = 1 << 20) -> None:
         """Drop tombstoned rows physically: surviving rows slide down in place, block by block (a staged
         block is at most ``block_rows`` rows, so the corpus never needs a second copy in HBM).  Chunk
-        indices are renumbered -- on a sharded corpus re-derive ``chunk_base`` of the later shards."""
+        indices are renumbered inside this shard's range; ``chunk_base`` does not move, so the other shards of
+        a ``ShardedIndex`` are unaffected (call ``ShardedIndex.refresh`` afterwards: it re-gathers the shard
+        ranges and the chunk-id tables)."""
         if self._alive is None:
             return
         with self._lock, torch.cuda.device(self.device):
+            self._invalidate_filters()
+            self._meta_inv = None
             dst = 0
             for r0 in range(0, self.n_rows, block_rows):
                 r1 = min(self.n_rows, r0 + block_rows)
@@ -411,6 +429,79 @@ class CorpusIndex:
                                             1 if round_fp16 else 0, _stream()), "rl_adapter_apply")
         return out
 
+    # ---- metadata filters resolved on the device (_search.py:82-95) -------------------------------------
+    def _metadata_index(self) -> dict[tuple[str, Any], np.ndarray]:
+        """Inverted index ``(key, value) -> chunk indices`` over ``chunk_metadata``, built in one pass (and
+        extended over appended chunks): a search then never walks the chunk table on the host."""
+        if self.chunk_metadata is None:
+            raise ValueError("metadata_filter given but the index holds no chunk metadata")
+        if self._meta_inv is None or self._meta_inv_chunks > self.n_chunks:
+            self._meta_inv, self._meta_inv_chunks = {}, 0
+        if self._meta_inv_chunks < self.n_chunks:
+            fresh: dict[tuple[str, Any], list[int]] = {}
+            for c in range(self._meta_inv_chunks, self.n_chunks):
+                for key, have in self.chunk_metadata[c].items():
+                    for v in (have if isinstance(have, (list, tuple)) else [have]):
+                        try:
+                            fresh.setdefault((key, v), []).append(c)
+                        except TypeError:   # unhashable metadata value: cannot be asked for by a MetadataFilter
+                            continue
+            for kv, lst in fresh.items():
+                arr = np.asarray(lst, dtype=np.int64)
+                old = self._meta_inv.get(kv)
+                self._meta_inv[kv] = arr if old is None else np.concatenate([old, arr])
+            self._meta_inv_chunks = self.n_chunks
+        return self._meta_inv
+
+    def filter_chunks(self, metadata_filter: dict[str, list[Any]]) -> tuple[torch.Tensor, int]:
+        """``(chunk_ok uint8 [n_chunks] on the device, number of matching live rows)`` for a normalised
+        filter ``{key: [values...]}``: a chunk matches when its metadata contains every requested value
+        (JSON containment on list-valued metadata, ``_search.py:82-95``).  Cached per filter until the
+        index changes."""
+        key = tuple(sorted((k, tuple(v)) for k, v in metadata_filter.items()))
+        with self._lock:
+            hit = self._filter_cache.get(key)
+            if hit is not None:
+                return hit
+            inv = self._metadata_index()
+            ok: np.ndarray | None = None
+            for k, wanted in metadata_filter.items():
+                for w in wanted:
+                    ids = inv.get((k, w), np.zeros(0, np.int64))
+                    ok = ids if ok is None else np.intersect1d(ok, ids, assume_unique=False)
+            ok = np.zeros(0, np.int64) if ok is None else np.unique(ok)
+            ok = ok[self._chunk_alive[ok]] if len(ok) else ok
+            n_rows = int((self.chunk_off[ok + 1] - self.chunk_off[ok]).sum()) if len(ok) else 0
+            with torch.cuda.device(self.device):
+                chunk_ok = torch.zeros(max(self.n_chunks, 1), dtype=torch.uint8, device=self.device)
+                if len(ok):
+                    chunk_ok.index_fill_(0, torch.from_numpy(ok).to(self.device), 1)
+            if len(self._filter_cache) >= 32:
+                self._filter_cache.pop(next(iter(self._filter_cache)))
+            self._filter_cache[key] = (chunk_ok, n_rows)
+            return chunk_ok, n_rows
+
+    def row_mask(self, chunk_ok: torch.Tensor | None) -> torch.Tensor | None:
+        """``rl_row_mask``: the per-row byte mask of a per-chunk filter, ANDed with the tombstones."""
+        if chunk_ok is None:
+            return self._alive
+        out = torch.empty(self.n_rows + 16, dtype=torch.uint8, device=self.device)[: self.n_rows]
+        with torch.cuda.device(self.device):
+            check(self.lib.rl_row_mask(_ptr(chunk_ok), _ptr(self.row_chunk), _ptr(self._alive), self.n_rows, _ptr(out),
+                                       _stream()), "rl_row_mask")
+        return out
+
+    def _invalidate_filters(self) -> None:
+        self._filter_cache.clear()
+        self._n_live_rows = None
+
+    @property
+    def n_live_rows(self) -> int:
+        """Rows that are not tombstoned (cached until the index changes)."""
+        if getattr(self, "_n_live_rows", None) is None:
+            self._n_live_rows = int(np.diff(self.chunk_off)[self._chunk_alive].sum()) if self.n_chunks else 0
+        return self._n_live_rows
+
     # ---- scan ---------------------------------------------------------------------------------------
     def _params(self, Q: torch.Tensor, k: int, num_hits: int, metric: str, algo: str,
                 row_allowed: torch.Tensor | None, flags: int, sample_stride: int, cand_cap: int) -> ScanParams:
@@ -427,12 +518,27 @@ class CorpusIndex:
             raise ValueError("storage='fp16' with the cosine metric needs rows with norm >= 0.5 (normalised embeddings)")
         return p
 
+    def _workspace(self, need: int) -> torch.Tensor:
+        """The workspace of the CURRENT stream, grown on demand (caller holds the lock)."""
+        key = _stream()
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            if ws is not None:
+                self.lib.rl_maxsim_release(_ptr(ws))
+                del self._ws[key]
+                ws = None  # free before the larger allocation
+            ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
     def scan(  # noqa: PLR0913
         self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
         row_allowed: torch.Tensor | None = None, flags: int = 0, sample_stride: int = 0, cand_cap: int = 0,
-        out: ScanResult | None = None,
+        out: ScanResult | None = None, mask_has_tombstones: bool = False,
     ) -> ScanResult:
-        """Asynchronous shard scan on the current stream: Q is float32 ``[B, d]`` on this device."""
+        """Asynchronous shard scan on the current stream: Q is float32 ``[B, d]`` on this device.
+        ``row_allowed`` is the optional per-row byte mask (``row_mask`` builds it from a metadata filter;
+        ``mask_has_tombstones`` says the tombstones are already folded in)."""
         if Q.dtype != torch.float32 or Q.ndim != 2 or Q.shape[1] != self.d or not Q.is_contiguous():
             raise ValueError(f"Q must be a contiguous float32 [B, {self.d}] tensor")
         if metric not in RL_METRIC:
@@ -440,15 +546,13 @@ class CorpusIndex:
         B = int(Q.shape[0])
         H = num_hits if num_hits > 0 else k
         with self._lock, torch.cuda.device(self.device):
-            if self._alive is not None:  # tombstoned rows are masked like a metadata filter
+            if self._alive is not None and not mask_has_tombstones:  # tombstoned rows are masked like a metadata filter
                 row_allowed = self._alive if row_allowed is None else (row_allowed & self._alive)
             p = self._params(Q, k, num_hits, metric, algo, row_allowed, flags, sample_stride, cand_cap)
             need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
             if need == 0 and B > 0:
                 raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = None
-                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            ws = self._workspace(need)
             if out is None:
                 out = ScanResult(
                     torch.empty((B, H), dtype=torch.float32, device=self.device),
@@ -456,9 +560,9 @@ class CorpusIndex:
                     torch.empty((B,), dtype=torch.int32, device=self.device),
                     torch.empty((B,), dtype=torch.int32, device=self.device), num_hits, k)
             check(self.lib.rl_maxsim_topk(C.byref(p), _ptr(out.hit_sim), _ptr(out.hit_chunk), _ptr(out.hit_count),
-                                          _ptr(out.status), _ptr(self._ws), self._ws.numel(), _stream()),
+                                          _ptr(out.status), _ptr(ws), ws.numel(), _stream()),
                   "rl_maxsim_topk")
-            self.last_params = p
+            self.last_params, self.last_ws = p, ws
         return out
 
     def count_at_least(  # noqa: PLR0913
@@ -480,24 +584,25 @@ class CorpusIndex:
             need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
             if need == 0 and B > 0:
                 raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = None
-                self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
-            check(self.lib.rl_maxsim_count_at_least(C.byref(p), _ptr(floor), int(bound), _ptr(counts), _ptr(self._ws),
-                                                    self._ws.numel(), _stream()), "rl_maxsim_count_at_least")
+            ws = self._workspace(need)
+            check(self.lib.rl_maxsim_count_at_least(C.byref(p), _ptr(floor), int(bound), _ptr(counts), _ptr(ws),
+                                                    ws.numel(), _stream()), "rl_maxsim_count_at_least")
         return counts
 
     def sum_over_shards(self, x: torch.Tensor) -> torch.Tensor:
         """A single shard is the whole corpus (``ShardedIndex`` all-reduces)."""
         return x
 
+    def max_over_shards(self, x: torch.Tensor) -> torch.Tensor:
+        return x
+
     def scan_stats(self) -> dict[str, int]:
         """Counters of the last scan (synchronises)."""
-        if self.last_params is None or self._ws is None:
+        if self.last_params is None or self.last_ws is None:
             return {}
         st = ScanStats()
         with torch.cuda.device(self.device):
-            check(self.lib.rl_maxsim_stats(C.byref(self.last_params), _ptr(self._ws), C.byref(st), _stream()),
+            check(self.lib.rl_maxsim_stats(C.byref(self.last_params), _ptr(self.last_ws), C.byref(st), _stream()),
                   "rl_maxsim_stats")
         return {name: int(getattr(st, name)) for name, _ in ScanStats._fields_}
 
@@ -505,56 +610,124 @@ class CorpusIndex:
         """Sampled approximate keys ``[B, n_sample_rows]`` of the last scan (test hook)."""
         n = C.c_int64(0)
         p = self.last_params
-        check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self._ws), None, C.byref(n), _stream()), "rl_maxsim_copy_dump")
+        check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self.last_ws), None, C.byref(n), _stream()), "rl_maxsim_copy_dump")
         out = torch.empty((int(p.B), int(n.value)), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self._ws), _ptr(out), C.byref(n), _stream()),
+            check(self.lib.rl_maxsim_copy_dump(C.byref(p), _ptr(self.last_ws), _ptr(out), C.byref(n), _stream()),
                   "rl_maxsim_copy_dump")
         return out
 
     def kernel_times_ms(self) -> dict[str, float]:
         """Stage times of the last scan made with ``flags=RL_FLAG_TIME_KERNELS`` (synchronises)."""
         ms = (C.c_float * 5)()
-        check(self.lib.rl_maxsim_kernel_times(_ptr(self._ws), ms), "rl_maxsim_kernel_times")
+        check(self.lib.rl_maxsim_kernel_times(_ptr(self.last_ws), ms), "rl_maxsim_kernel_times")
         return dict(zip(("prep", "sample_scan", "select", "main_scan", "finalize"), (float(x) for x in ms), strict=True))
 
     def scan_checked(self, Q: torch.Tensor, **kw: Any) -> ScanResult:
-        """Scan, read the status back and resolve what the single pass could not:
+        """Scan, read the status back and resolve a candidate-list overflow (adversarial corpus order, or
+        more near-ties at the cut than the list holds): first re-run with the tightened thresholds the
+        first pass left in the workspace, then with a four times larger list, until nothing overflows
+        (the list is bounded by the shard's row count, so this terminates).  The index lock is held
+        throughout: the retry reads thresholds that live in this stream's workspace.
 
-        * candidate-list overflow (adversarial corpus order): re-run with the tightened thresholds the
-          first pass left in the workspace, up to four times;
-        * more than ``RL_MAX_SURVIVORS`` vectors inside the coarse scan's error band of the cut (dense
-          low-dimensional data, thousands of near-duplicates): re-run those queries with the float32
-          scan, whose band is an order of magnitude narrower.
-
-        Anything still unresolved raises -- a silently truncated survivor list could drop a true hit."""
+        More than ``RL_MAX_SURVIVORS`` vectors inside the coarse scan's error band of the cut (tight
+        clusters, thousands of near-duplicates) need no retry: ``finalize`` streams them."""
         kw = dict(kw)
         out = kw.pop("out", None)
-        res = self.scan(Q, **kw, out=out)
-        status = res.status.cpu()
-        for _ in range(4):
-            if not bool((status & RL_STATUS_CAND_OVERFLOW).any()):
-                break
-            res = self.scan(Q, **{**kw, "flags": kw.get("flags", 0) | RL_FLAG_REUSE_THRESHOLDS}, out=res)
-            status = res.status.cpu()
-        if bool((status & RL_STATUS_CAND_OVERFLOW).any()):
-            raise _lib.RagliteB200Error("candidate lists still overflow after four threshold refinements; pass a larger cand_cap")
-        tie = (status & RL_STATUS_TIE_OVERFLOW) != 0
-        if bool(tie.any()):
-            if self.storage != "fp32" or kw.get("algo", "auto") == "fp32":
-                raise _lib.RagliteB200Error(
-                    f"{int(tie.sum())} queries have more than {RL_MAX_SURVIVORS} vectors within the scan's error band of "
-                    "the cut (massive ties): the ranking cannot be resolved")
-            rows = torch.nonzero(tie).flatten().to(self.device)
-            sub = self.scan_checked(Q[rows].contiguous(),
-                                    **{**kw, "algo": "fp32", "flags": kw.get("flags", 0) & ~RL_FLAG_REUSE_THRESHOLDS})
-            res.hit_sim[rows], res.hit_chunk[rows] = sub.hit_sim, sub.hit_chunk
-            res.hit_count[rows], res.status[rows] = sub.hit_count, sub.status
-        return res
+        base_flags = kw.pop("flags", 0)
+        cap = int(kw.pop("cand_cap", 0))
+        with self._lock:
+            res = self.scan(Q, **kw, flags=base_flags, cand_cap=cap, out=out)
+            for attempt in range(1, 16):
+                if not bool((res.status & RL_STATUS_CAND_OVERFLOW).any()):   # (synchronises)
+                    return res
+                cap, flags = next_overflow_attempt(self, attempt, cap, base_flags)
+                res = self.scan(Q, **kw, flags=flags, cand_cap=cap, out=res)
+        raise _lib.RagliteB200Error("candidate lists still overflow with a list as large as the shard")
+
+    def search_pipeline(  # noqa: PLR0913
+        self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
+        row_allowed: torch.Tensor | None = None, mask_has_tombstones: bool = False, flags: int = 0, cand_cap: int = 0,
+        sample_stride: int = 0, rank_first_limit: int | None = None,
+    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """scan -> [rank-then-filter cut] -> GROUP BY / top-k, all enqueued on the current stream; returns
+        device tensors ``(sim [B, k], chunk [B, k], count [B], status [B])`` without synchronising."""
+        res = self.scan(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=row_allowed,
+                        mask_has_tombstones=mask_has_tombstones, flags=flags, cand_cap=cand_cap, sample_stride=sample_stride)
+        hit_count = res.hit_count
+        if rank_first_limit is not None:
+            hit_count = limit_hits_to_nearest(self, Q, res.hit_sim[None], hit_count[None], k=k, num_hits=num_hits,
+                                              metric=metric, algo=algo, limit=rank_first_limit)[0]
+        sim, chunk, count = merge_hits(res.hit_sim, res.hit_chunk, hit_count, num_hits=num_hits, k=k)
+        return sim, chunk, count, res.status
 
     def chunk_id_of(self, global_chunk: int) -> ChunkId:
         local = int(global_chunk) - self.chunk_base
         return self.chunk_ids[local] if self.chunk_ids is not None else str(int(global_chunk))
+
+    # ---- results to the host in one copy ------------------------------------------------------------------
+    def to_host(self, sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor
+                ) -> tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+        """One device->host copy (pinned staging buffer) of a merged result plus the OR of the status words,
+        then ONE stream synchronisation -- the only host sync of a search."""
+        B, k = int(sim.shape[0]), int(sim.shape[1])
+        st_any = status.reshape(-1).to(torch.int32)
+        st_any = st_any.max().reshape(1) if st_any.numel() else torch.zeros(1, dtype=torch.int32, device=sim.device)
+        parts = [chunk.contiguous().view(torch.uint8).reshape(-1), sim.contiguous().view(torch.uint8).reshape(-1),
+                 count.to(torch.int32).contiguous().view(torch.uint8).reshape(-1), st_any.view(torch.uint8).reshape(-1)]
+        dev = torch.cat(parts)
+        n = int(dev.numel())
+        host = self._pinned.get(n)
+        if host is None:
+            if len(self._pinned) >= 8:
+                self._pinned.pop(next(iter(self._pinned)))
+            host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            self._pinned[n] = host
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        raw = host.numpy()
+        n8, n4 = B * k * 8, B * k * 4
+        ids = raw[:n8].view(np.int64).reshape(B, k).copy()
+        sims = raw[n8:n8 + n4].view(np.float32).reshape(B, k).copy()
+        counts = raw[n8 + n4:n8 + n4 + B * 4].view(np.int32).copy()
+        return ids, sims, counts, int(raw[n8 + n4 + B * 4:].view(np.int32)[0])
+
+
+def next_overflow_attempt(local: "CorpusIndex", attempt: int, cap: int, base_flags: int) -> tuple[int, int]:
+    """Retry policy after a candidate-list overflow: odd attempts re-run with the thresholds the failed
+    pass wrote (``RL_FLAG_REUSE_THRESHOLDS``, same list size); even attempts start over with a list four
+    times as large (a larger workspace: thresholds are not carried over)."""
+    if attempt % 2 == 1:
+        return cap, base_flags | RL_FLAG_REUSE_THRESHOLDS
+    if cap <= 0:
+        cap = int(local.scan_stats().get("cand_cap", 1024))
+    if cap >= local.n_rows + 1024:
+        raise _lib.RagliteB200Error("candidate lists still overflow with a list as large as the shard")
+    return min(cap * 4, local.n_rows + 1024), base_flags & ~RL_FLAG_REUSE_THRESHOLDS
+
+
+def search_to_host(  # noqa: PLR0913
+    index: Any, Q: torch.Tensor, *, k: int, num_hits: int, metric: str, algo: str = "auto",
+    chunk_ok: torch.Tensor | None = None, rank_first_limit: int | None = None,
+) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """The whole search for a (sharded or single) index with ONE host synchronisation: scan ->
+    [all-gather] -> merge are enqueued back to back, results and status come back in one pinned copy,
+    and only then is the (rare) candidate overflow looked at.  On a sharded corpus the status words
+    travel with the gathered hit lists, so every rank takes the same retry decision without a second
+    collective.  Holds the index lock from the first launch to the verified result."""
+    local: CorpusIndex = getattr(index, "local", index)
+    with local._lock, torch.cuda.device(local.device):
+        mask = local.row_mask(chunk_ok)
+        cap, flags = 0, 0
+        for attempt in range(16):
+            sim, chunk, count, status = index.search_pipeline(
+                Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=mask, mask_has_tombstones=True,
+                flags=flags, cand_cap=cap, rank_first_limit=rank_first_limit)
+            ids, sims, counts, st = local.to_host(sim, chunk, count, status)
+            if not st & RL_STATUS_CAND_OVERFLOW:
+                return ids, sims, counts
+            cap, flags = next_overflow_attempt(local, attempt + 1, cap, 0)
+    raise _lib.RagliteB200Error("candidate lists still overflow with a list as large as the shard")
 
 
 def merge_hits(  # noqa: PLR0913
@@ -606,7 +779,9 @@ def limit_hits_to_nearest(  # noqa: PLR0913
     Qn = Q[need].contiguous()
     lo = floor[need].clone()
     qn = Qn.double().norm(dim=1)
-    max_norm = float(local.stats[0])
+    # The bracket must be identical on every rank (the counts are summed over shards against one `mid`):
+    # the largest row norm is taken over all shards, not this rank's own.
+    max_norm = index.max_over_shards(local.stats[0:1].to(torch.float32).clone()).double()
     hi = (1.0 + qn * max_norm * 1.001 + 1e-3).float() if metric == "dot" else torch.full_like(lo, 1.0 + 1e-3)
     exact_algo = "fp32" if local.storage == "fp32" else algo   # tightest keys this storage allows
     for _ in range(bisect_steps):

@@ -19,11 +19,10 @@ RL_FLAG_TIME_KERNELS = 2
 RL_STATUS_CAND_OVERFLOW = 1
 RL_STATUS_TIE_OVERFLOW = 2
 RL_MAX_SURVIVORS = 4096   # finalize window (include/raglite_b200.h)
-RL_MAX_SURVIVORS = 4096
 
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
-    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_copy_dump", "rl_topk_merge",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_row_mask",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
@@ -83,6 +82,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_maxsim_count_at_least.argtypes = [C.POINTER(ScanParams), vp, C.c_int, vp, vp, C.c_size_t, vp]
     lib.rl_maxsim_stats.argtypes = [C.POINTER(ScanParams), vp, C.POINTER(ScanStats), vp]
     lib.rl_maxsim_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.rl_maxsim_release.argtypes = [vp]
+    lib.rl_row_mask.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.rl_maxsim_copy_dump.argtypes = [C.POINTER(ScanParams), vp, vp, C.POINTER(C.c_int64), vp]
     lib.rl_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.rl_segment_mean_pool.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ._config import RAGLiteConfig
-from ._index import Chunk, CorpusIndex, get_index, limit_hits_to_nearest, merge_hits
+from ._index import Chunk, CorpusIndex, get_index, search_to_host
 from ._typing import ChunkId, FloatVector, MetadataFilter
 
 REFERENCE_CHUNK_MAX_SIZE = 2048  # RAGLiteConfig.chunk_max_size class default (_config.py:67)
@@ -39,26 +39,14 @@ FILTER_FIRST_MAX_ROWS = 100_000   # metadata_count <= 100_000: filter, then rank
 RANK_FIRST_LIMIT = 1_000_000      # otherwise: the 1_000_000 nearest vectors, then the filter (_search.py:126)
 
 
-def _allowed_rows(index: Any, metadata_filter: dict[str, list[Any]] | None) -> torch.Tensor | None:
-    """Rows whose chunk metadata contains every requested value (JSON containment on list-valued
-    metadata, ``_search.py:82-95``) as the byte mask the scan reads."""
+def _filter_on_device(index: Any, metadata_filter: dict[str, list[Any]] | None) -> tuple[torch.Tensor | None, int]:
+    """The metadata filter as a per-chunk byte mask on the device plus the number of live rows it
+    matches on this shard (``CorpusIndex.filter_chunks``: an inverted index over the chunk metadata,
+    built once and cached per filter -- a search never walks the chunk table on the host)."""
     if not metadata_filter:
-        return None
+        return None, 0
     local: CorpusIndex = getattr(index, "local", index)
-    if local.chunk_metadata is None:
-        raise ValueError("metadata_filter given but the index holds no chunk metadata")
-    ok = np.zeros(local.n_chunks, dtype=bool)
-    for c, meta in enumerate(local.chunk_metadata):
-        good = True
-        for key, wanted in metadata_filter.items():
-            have = meta.get(key)
-            have = have if isinstance(have, (list, tuple)) else [have]
-            if not all(w in have for w in wanted):
-                good = False
-                break
-        ok[c] = good
-    rows = np.repeat(ok, np.diff(local.chunk_off)).astype(np.uint8)
-    return torch.from_numpy(rows).to(local.device)
+    return local.filter_chunks(metadata_filter)
 
 
 def vector_search_batch(  # noqa: PLR0913
@@ -77,7 +65,8 @@ def vector_search_batch(  # noqa: PLR0913
 
     Returns host arrays ``(chunk_index[B, k] int64 (-1 padded), sim[B, k] float32, count[B])``.
     ``exact_maxsim=True`` ranks by exact per-chunk MaxSim instead of the reference's
-    top-``num_hits``-vectors semantics.
+    top-``num_hits``-vectors semantics.  Host work per call is O(B): the query upload, kernel launches,
+    one pinned device->host copy of the results and one stream synchronisation.
     """
     config = config or RAGLiteConfig()
     index = index if index is not None else get_index(config)
@@ -91,36 +80,27 @@ def vector_search_batch(  # noqa: PLR0913
         raise ValueError("queries must be [B, d]")
     k = int(num_results)
     B = int(Q.shape[0])
-    if local.n_live_chunks == 0 and not hasattr(index, "search_device"):
+    sharded = hasattr(index, "group")
+    if local.n_live_chunks == 0 and not sharded:
         return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
     if config.vector_search_query_adapter and local.query_adapter is not None:
         Q = local.apply_adapter(Q, round_fp16=queries_are_fp16)
     num_hits = 0 if exact_maxsim else num_hits_rule(k, oversample, config.chunk_max_size)
     if not exact_maxsim and num_hits == 0:  # round(oversample * size / 2048) == 0 -> LIMIT 0
         return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
-    allowed = _allowed_rows(index, _adapt_metadata(metadata_filter))
+    chunk_ok, n_match = _filter_on_device(index, _adapt_metadata(metadata_filter))
     metric = config.vector_search_distance_metric
     # Which metadata branch the reference would take (_search.py:96-143): many matching rows in a corpus
     # of more than 1M vectors -> only filtered hits among the 1M nearest vectors overall count.
     rank_first_limit = None
-    if allowed is not None and num_hits > 0:
-        live = local._alive   # tombstones, if any
-        n_match = (allowed if live is None else allowed & live).sum(dtype=torch.int64)
-        n_rows = live.sum(dtype=torch.int64) if live is not None else torch.tensor(local.n_rows, device=local.device)
-        totals = index.sum_over_shards(torch.stack([n_match, n_rows.to(torch.int64)])).tolist()
+    if chunk_ok is not None and num_hits > 0:
+        totals = [n_match, local.n_live_rows]
+        if sharded:
+            totals = index.sum_over_shards(torch.tensor(totals, dtype=torch.int64, device=local.device)).tolist()
         if totals[0] > FILTER_FIRST_MAX_ROWS and totals[1] > RANK_FIRST_LIMIT:
             rank_first_limit = RANK_FIRST_LIMIT
-    if hasattr(index, "search_device"):  # sharded across ranks
-        sim, chunk, count = index.search_device(Q, k=k, num_hits=num_hits, metric=metric, algo=algo,
-                                                row_allowed=allowed, checked=True, rank_first_limit=rank_first_limit)
-    else:
-        res = local.scan_checked(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=allowed)
-        hit_count = res.hit_count
-        if rank_first_limit is not None:
-            hit_count = limit_hits_to_nearest(local, Q, res.hit_sim[None], hit_count[None], k=k, num_hits=num_hits,
-                                              metric=metric, algo=algo, limit=rank_first_limit)[0]
-        sim, chunk, count = merge_hits(res.hit_sim, res.hit_chunk, hit_count, num_hits=num_hits, k=k)
-    return chunk.cpu().numpy(), sim.cpu().numpy(), count.cpu().numpy()
+    return search_to_host(index, Q, k=k, num_hits=num_hits, metric=metric, algo=algo, chunk_ok=chunk_ok,
+                          rank_first_limit=rank_first_limit)
 
 
 def vector_search(

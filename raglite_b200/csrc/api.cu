@@ -151,7 +151,7 @@ static int device_sm_count(int* out) {
 
 using namespace rl;
 
-extern "C" int rl_version(void) { return 100; }
+extern "C" int rl_version(void) { return 101; }
 extern "C" const char* rl_last_error(void) { return g_err; }
 
 extern "C" int rl_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes) {
@@ -266,7 +266,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   mark(4);
 
   FinalizeArgs f;
-  f.E = p->E; f.row_chunk = p->row_chunk; f.Q = p->Q; f.q_sq = q_sq; f.eps = eps; f.cand = cand; f.cand_cnt = cand_cnt;
+  f.E = p->E; f.row_chunk = p->row_chunk; f.Q = p->Q; f.q_sq = q_sq; f.eps = eps; f.cand = cand; f.cand_rw = cand; f.cand_cnt = cand_cnt;
   f.thr_out = thr_out; f.hit_sim = hit_sim; f.hit_chunk = hit_chunk; f.hit_count = hit_count; f.status = status;
   f.n_surv = n_surv; f.header = hdr; f.ld = p->ld; f.chunk_base = p->chunk_base; f.n_sample_rows = L.n_sample_rows;
   f.d = p->d; f.metric = p->metric; f.cap = L.cap; f.mode_sql = L.mode_sql;
@@ -360,6 +360,19 @@ extern "C" int rl_maxsim_kernel_times(const void* workspace, float* ms) {
   return RL_OK;
 }
 
+extern "C" int rl_maxsim_release(const void* workspace) {
+  // Drops the CUDA events rl_maxsim_topk created for this workspace (RL_FLAG_TIME_KERNELS); call it
+  // before the workspace memory is freed or handed to another use.  A workspace never timed is a no-op.
+  std::lock_guard<std::mutex> lock(g_ev_mutex);
+  auto it = g_events.find(workspace);
+  if (it == g_events.end()) return RL_OK;
+  if (it->second.valid)
+    for (int r = 0; r < kEventRing; ++r)
+      for (int i = 0; i < kNumStageEvents; ++i) cudaEventDestroy(it->second.ev[r][i]);
+  g_events.erase(it);
+  return RL_OK;
+}
+
 extern "C" int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   RL_REQUIRE(p && workspace && out, RL_EINVAL, "rl_maxsim_stats: null pointer");
@@ -418,5 +431,6 @@ extern "C" int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, con
   MergeArgs m;
   m.hit_sim = hit_sim; m.hit_chunk = hit_chunk; m.hit_count = hit_count; m.out_sim = out_sim;
   m.out_chunk = out_chunk; m.out_count = out_count; m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k;
+  m.win = 0;
   return launch_merge(m, (cudaStream_t)stream);
 }

@@ -188,6 +188,43 @@ __global__ void __launch_bounds__(256) segment_mean_pool_kernel(const float* __r
   }
 }
 
+
+// out[row] = chunk_ok[row_chunk[row]] (all-ones when chunk_ok is null) AND alive[row] (when given): the
+// per-row byte mask the scan epilogue reads.  chunk_ok is the metadata filter resolved per chunk
+// (reference _search.py:82-95), alive the tombstones of deleted chunks (_delete.py:146-152).
+// 16 rows per thread: four int4 loads of owners, one 16-byte load of tombstones, one 16-byte store.
+__global__ void __launch_bounds__(256) row_mask_kernel(const uint8_t* __restrict__ chunk_ok,
+                                                       const int32_t* __restrict__ row_chunk,
+                                                       const uint8_t* __restrict__ alive, int64_t n_rows,
+                                                       uint8_t* __restrict__ out) {
+  const int64_t n16 = n_rows / 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t w[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};
+    if (chunk_ok != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(row_chunk) + i * 4 + q);
+        w[q] = (uint32_t)(chunk_ok[c.x] != 0) | ((uint32_t)(chunk_ok[c.y] != 0) << 8) |
+               ((uint32_t)(chunk_ok[c.z] != 0) << 16) | ((uint32_t)(chunk_ok[c.w] != 0) << 24);
+      }
+    }
+    if (alive != nullptr) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(alive) + i);
+      // any non-zero tombstone byte counts as alive: normalise each byte to 0/1 before the AND
+      auto norm = [](uint32_t x) { return ((x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4) | (x >> 5) | (x >> 6) | (x >> 7)) & 0x01010101u); };
+      w[0] &= norm(a.x); w[1] &= norm(a.y); w[2] &= norm(a.z); w[3] &= norm(a.w);
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // ragged tail (n_rows % 16 rows)
+  const int64_t t0 = n16 * 16;
+  for (int64_t r = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t v = chunk_ok != nullptr ? (uint8_t)(chunk_ok[row_chunk[r]] != 0) : (uint8_t)1;
+    if (alive != nullptr && alive[r] == 0) v = 0;
+    out[r] = v;
+  }
+}
+
 }  // namespace rl
 
 using namespace rl;
@@ -256,6 +293,21 @@ extern "C" int rl_segment_mean_pool(const float* X, int64_t ld, int d, const int
   RL_CUDA_CHECK(cudaFuncSetAttribute(segment_mean_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   segment_mean_pool_kernel<<<S, 256, smem, (cudaStream_t)stream>>>(X, ld, d, row_begin, row_end, normalize,
                                                                      reinterpret_cast<__half*>(out));
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+extern "C" int rl_row_mask(const uint8_t* chunk_ok, const int32_t* row_chunk, const uint8_t* alive, int64_t n_rows,
+                           uint8_t* out, void* stream) {
+  RL_REQUIRE(n_rows >= 0, RL_EINVAL, "rl_row_mask: bad n_rows");
+  if (n_rows == 0) return RL_OK;
+  RL_REQUIRE(out && (chunk_ok == nullptr || row_chunk != nullptr), RL_EINVAL, "rl_row_mask: null pointer");
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(row_chunk) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(alive) & 15) == 0,
+             RL_EINVAL, "rl_row_mask: row_chunk, alive and out must be 16-byte aligned");
+  const int64_t blocks = (n_rows / 16 + 255) / 256 + 1;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  row_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(chunk_ok, row_chunk, alive, n_rows, out);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }

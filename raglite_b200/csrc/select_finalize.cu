@@ -493,17 +493,13 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
   if (threadIdx.x == 0) f.thr_out[b] = cut;
   __syncthreads();
   const int ns_all = s_count;
-  const int ns = min(ns_all, RL_MAX_SURVIVORS);
-  if (ns_all > RL_MAX_SURVIVORS) st |= RL_STATUS_TIE_OVERFLOW;
-  int npow2 = 1;
-  while (npow2 < ns) npow2 <<= 1;
+  int ns = min(ns_all, RL_MAX_SURVIVORS);
 
-  // Exact rescoring: one warp per survivor row, float64 dot / norm, warp-shuffle reduction.
+  // Exact rescoring of one row by one warp: float64 dot / norm, warp-shuffle reduction.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const double nq = f.q_sq[b];
   const bool vec = (f.d % 4 == 0) && (f.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.E) & 15) == 0);
-  for (int s = warp; s < ns; s += nwarps) {
-    const int32_t row = rows[s];
+  auto exact_row_sim = [&](int32_t row) -> float {   // all 32 lanes call it; every lane gets the result
     const float* e = f.E + (int64_t)row * f.ld;
     double dot = 0.0, ne = 0.0;
     if (f.e_f16) {   // float16 storage: 8 halves per 16-byte load (d % 8 == 0)
@@ -534,11 +530,74 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
     }
     dot = warp_sum_d(dot);
     ne = warp_sum_d(ne);
-    if (lane == 0) {
-      const float sim = exact_sim(f.metric, dot, ne, nq);
-      keys[s] = ((uint64_t)(~f2ord(sim)) << 32) | (uint32_t)row;  // ascending: sim desc, row asc
+    return exact_sim(f.metric, dot, ne, nq);
+  };
+
+  if (ns_all <= RL_MAX_SURVIVORS) {
+    for (int s = warp; s < ns; s += nwarps) {
+      const int32_t row = rows[s];
+      const float sim = exact_row_sim(row);
+      if (lane == 0) keys[s] = ((uint64_t)(~f2ord(sim)) << 32) | (uint32_t)row;  // ascending: sim desc, row asc
     }
+  } else {
+    // More rows than the shared-memory window sit inside the coarse key's error band of the cut (tight
+    // clusters / near-duplicates: thousands of vectors within 2 eps of each other).  Stream instead:
+    // (1) every survivor in the global candidate list is rescored exactly and its record overwritten
+    //     with the order-preserving bits of the exact similarity (0 = not a survivor),
+    // (2) a radix select over the 64-bit composite (sim desc, row asc) -- all composites are distinct --
+    //     narrows the list to the sel_k best plus at most a window's worth of ties in the last digit,
+    // (3) those are gathered into the window and take the normal sort / GROUP BY path below.
+    Cand* wc = f.cand_rw + (size_t)b * f.cap;
+    for (int i = warp; i < n; i += nwarps) {
+      const Cand c = wc[i];                      // same address for the whole warp: one broadcast load
+      uint32_t o = 0u;
+      if (c.key >= cut) o = f2ord(exact_row_sim(c.row));
+      if (lane == 0) wc[i].key = __uint_as_float(o);
+    }
+    __syncthreads();
+    auto comp_of = [&](int i) -> uint64_t {      // larger = better; 0 for non-survivors
+      const Cand c = wc[i];
+      const uint32_t o = __float_as_uint(c.key);
+      return o == 0u ? 0ull : (((uint64_t)o << 32) | (uint32_t)(~(uint32_t)c.row));
+    };
+    uint64_t prefix = 0;      // value of the top `bits` bits of the sel_k-th largest composite
+    int bits = 0, need = f.sel_k;
+    while (bits < 64) {
+      const int w = min(12, 64 - bits);
+      const int shift = 64 - bits - w;
+      for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t c = comp_of(i);
+        if (c != 0ull && (bits == 0 || (c >> (64 - bits)) == prefix)) atomicAdd(&hist[(uint32_t)(c >> shift) & ((1u << w) - 1u)], 1u);
+      }
+      __syncthreads();
+      find_bin_from_top(hist, need, res);
+      __syncthreads();
+      const int bin = res[0] < 0 ? 0 : res[0];     // < 0: fewer than `need` survivors left -> take everything
+      const int above = res[0] < 0 ? 0 : res[1];
+      const int in_bin = (int)hist[bin];
+      __syncthreads();
+      prefix = (prefix << w) | (uint64_t)bin;
+      bits += w;
+      need -= above;
+      // survivors with top bits > prefix number sel_k - need; those == prefix number in_bin
+      if (res[0] < 0 || (f.sel_k - need) + in_bin <= RL_MAX_SURVIVORS) break;
+    }
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t c = comp_of(i);
+      if (c != 0ull && (c >> (64 - bits)) >= prefix) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < RL_MAX_SURVIVORS) keys[pos] = ~c;   // ~composite = (~ord(sim)) << 32 | row
+      }
+    }
+    __syncthreads();
+    ns = min(s_count, RL_MAX_SURVIVORS);
   }
+  int npow2 = 1;
+  while (npow2 < ns) npow2 <<= 1;
   for (int i = ns + threadIdx.x; i < npow2; i += blockDim.x) keys[i] = ~0ull;
   __syncthreads();
   bitonic_sort_u64(keys, npow2);
@@ -587,10 +646,11 @@ constexpr int kMergeMax = 8192;
 
 __global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);            // [kMergeMax]
-  int64_t* chunk = reinterpret_cast<int64_t*>(keys + kMergeMax);     // [kMergeMax]
-  uint8_t* flags = reinterpret_cast<uint8_t*>(chunk + kMergeMax);    // [kMergeMax]
-  int* pos = reinterpret_cast<int*>(flags + kMergeMax);              // [kMergeMax]
+  const int win = m.win;   // power of two >= R * H (<= kMergeMax): the arrays are sized by the actual problem
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);      // [win]
+  int64_t* chunk = reinterpret_cast<int64_t*>(keys + win);     // [win]
+  int* pos = reinterpret_cast<int*>(chunk + win);              // [win]
+  uint8_t* flags = reinterpret_cast<uint8_t*>(pos + win);      // [win]
   __shared__ int s_n;
   const int b = blockIdx.x;
   if (threadIdx.x == 0) s_n = 0;
@@ -695,10 +755,15 @@ int launch_finalize(const FinalizeArgs& f, int B, cudaStream_t stream) {
   return RL_OK;
 }
 
-int launch_merge(const MergeArgs& m, cudaStream_t stream) {
+int launch_merge(const MergeArgs& m_in, cudaStream_t stream) {
+  MergeArgs m = m_in;
   RL_REQUIRE((int64_t)m.R * m.H <= kMergeMax, RL_EUNSUPPORTED, "rl_topk_merge: R*H=%lld exceeds %d",
              (long long)m.R * m.H, kMergeMax);
-  const size_t smem = (size_t)kMergeMax * (8 + 8 + 1 + 4);
+  int win = 32;
+  while (win < m.R * m.H) win <<= 1;
+  m.win = win;
+  // sized by the problem, not by the cap: R*H = 3200 -> 86 KB -> two CTAs per SM, a 256-query batch is one wave
+  const size_t smem = (size_t)win * (8 + 8 + 4 + 1);
   RL_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_kernel<<<m.B, kSelThreads, smem, stream>>>(m);
   RL_CUDA_CHECK(cudaGetLastError());

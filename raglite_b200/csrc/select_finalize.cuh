@@ -24,6 +24,7 @@ struct FinalizeArgs {
   const double* q_sq;         // [B]
   const float* eps;           // [B]
   const Cand* cand;
+  Cand* cand_rw;              // same list, writable: the streaming survivor path rescores in place
   const int32_t* cand_cnt;
   float* thr_out;             // [B] cut usable as the next emission threshold
   float* hit_sim;             // [B, H]
@@ -44,6 +45,7 @@ struct MergeArgs {
   int64_t* out_chunk;         // [B, k]
   int32_t* out_count;         // [B]
   int32_t R, B, H, num_hits, k;
+  int32_t win;                // set by launch_merge: power of two >= R * H
 };
 
 constexpr int kFinalizeScratch = 20480;  // histogram (16 KB) / flags + positions (20 KB)

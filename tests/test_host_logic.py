@@ -186,19 +186,25 @@ def test_csr_from_row_chunk_ids_follows_the_table_layout():
 
 
 def test_scan_checked_resolves_or_raises():
-    """Host control flow around the status bits: threshold-refinement retries, float32 re-scan of the
-    queries whose survivor window overflowed, and loud failure for whatever stays unresolved."""
+    """Host control flow around the status bits: a candidate overflow is retried first with the
+    thresholds the failed pass wrote, then with a four times larger list, until the list is as large as
+    the shard; the index lock is held throughout."""
+    import threading
+
     import torch
 
     from raglite_b200 import _lib
     from raglite_b200._index import CorpusIndex, ScanResult
 
-    def fake_index(script):
+    def fake_index(script, n_rows=100_000):
         idx = object.__new__(CorpusIndex)
-        idx.storage, idx.device, idx.calls = "fp32", torch.device("cpu"), []
+        idx.storage, idx.device, idx.calls, idx.n_rows = "fp32", torch.device("cpu"), [], n_rows
+        idx._lock = threading.RLock()
+        idx.scan_stats = lambda: {"cand_cap": 1000}
 
         def scan(Q, *, out=None, **kw):
-            idx.calls.append((int(Q.shape[0]), kw.get("algo", "auto"), kw.get("flags", 0)))
+            assert idx._lock._is_owned()   # retries run under the index lock
+            idx.calls.append((kw.get("flags", 0), kw.get("cand_cap", 0)))
             status = torch.tensor(script(len(idx.calls), int(Q.shape[0]), kw), dtype=torch.int32)
             B = int(Q.shape[0])
             tag = float(len(idx.calls))
@@ -209,28 +215,22 @@ def test_scan_checked_resolves_or_raises():
         return idx
 
     Q = torch.zeros((3, 4))
+    REUSE = _lib.RL_FLAG_REUSE_THRESHOLDS
     # clean first pass
     idx = fake_index(lambda n, B, kw: [0] * B)
     assert idx.scan_checked(Q, k=1, num_hits=2).hit_sim[0, 0] == 1.0 and len(idx.calls) == 1
-    # candidate overflow twice, then clean: retries reuse the thresholds
-    idx = fake_index(lambda n, B, kw: [1, 0, 0] if n < 3 else [0] * B)
+    # overflow, cleared by the threshold-reuse retry
+    idx = fake_index(lambda n, B, kw: [1, 0, 0] if n < 2 else [0] * B)
     idx.scan_checked(Q, k=1, num_hits=2)
-    assert [c[2] for c in idx.calls] == [0, _lib.RL_FLAG_REUSE_THRESHOLDS, _lib.RL_FLAG_REUSE_THRESHOLDS]
-    # candidate overflow that never clears -> error
-    idx = fake_index(lambda n, B, kw: [1] * B)
+    assert idx.calls == [(0, 0), (REUSE, 0)]
+    # overflow that needs a larger list: reuse -> 4x list (fresh thresholds) -> reuse -> 16x ...
+    idx = fake_index(lambda n, B, kw: [1, 0, 0] if n < 5 else [0] * B)
+    idx.scan_checked(Q, k=1, num_hits=2)
+    assert idx.calls == [(0, 0), (REUSE, 0), (0, 4000), (REUSE, 4000), (0, 16000)]
+    # overflow that never clears: the list grows up to the shard size, then a loud failure
+    idx = fake_index(lambda n, B, kw: [1] * B, n_rows=10_000)
     with pytest.raises(_lib.RagliteB200Error):
         idx.scan_checked(Q, k=1, num_hits=2)
-    assert len(idx.calls) == 5
-    # survivor-window overflow on query 1: that query alone is re-scanned with the float32 kernel
-    idx = fake_index(lambda n, B, kw: [0, 2, 0] if kw.get("algo", "auto") != "fp32" else [0] * B)
-    res = idx.scan_checked(Q, k=1, num_hits=2, algo="tcgen05")
-    assert idx.calls == [(3, "tcgen05", 0), (1, "fp32", 0)]
-    assert res.hit_sim[:, 0].tolist() == [1.0, 2.0, 1.0] and res.status.tolist() == [0, 0, 0]
-    # ... and if the float32 scan cannot resolve it either, or the storage is fp16 -> error
-    idx = fake_index(lambda n, B, kw: [2] * B)
-    with pytest.raises(_lib.RagliteB200Error):
-        idx.scan_checked(Q, k=1, num_hits=2)
-    idx = fake_index(lambda n, B, kw: [0, 2, 0])
-    idx.storage = "fp16"
-    with pytest.raises(_lib.RagliteB200Error):
-        idx.scan_checked(Q, k=1, num_hits=2)
+    assert max(c[1] for c in idx.calls) == 10_000 + 1024
+
+
