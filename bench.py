@@ -46,6 +46,8 @@ WORKLOADS = {
     "c2": dict(chunks=100_000, vecs=8, dim=384, batch=256, k=20,
                desc="BASELINE configs[1]: 100k chunks x 8 vecs x 384-d fp32, batch 256, top-20"),
     "tiny": dict(chunks=20_000, vecs=8, dim=128, batch=64, k=10, desc="debug"),
+    "pool": dict(chunks=0, vecs=0, dim=1024, batch=2048, k=0,
+                 desc="late-chunking pool (_embed.py:119-140): 2048 segments x 496 token rows x 1024-d fp32 -> per-sentence mean, L2, fp16"),
     "c5": dict(chunks=0, vecs=0, dim=384, batch=1024, k=100,
                desc="BASELINE configs[4]: cross-encoder rerank, MiniLM-L12-H384, 1024 queries x 100 candidates (seeded weights)"),
 }
@@ -71,6 +73,10 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0)
+    ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"],
+                    help="clustered: tight clusters of near-duplicates + low-rank background, float16-rounded (tests/synth.py)")
+    ap.add_argument("--check-queries", type=int, default=16, help="queries compared with the oracle after the timed region")
+    ap.add_argument("--filtered", action="store_true", help="also time metadata-filtered searches (both reference branches)")
     return ap.parse_args()
 
 
@@ -166,7 +172,8 @@ def cpu_reference_rate(w: dict, sample_chunks: int, reps: int, seed: int = 0) ->
     Q = make_queries(E, w["batch"], seed=seed + 1)
     times = []
     with limiter:
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1]) if threadpool_info else want
+        # threads actually used: the BLAS pool after the limit (never more than the cores this process may run on)
+        threads = min(want, max([i.get("num_threads", 1) for i in threadpool_info()] + [1])) if threadpool_info else want
         blas_batch_topk(E[: 1024 * w["vecs"]], w["vecs"], Q[:8], min(w["k"], 64), num_hits=w["num_hits"])  # warm BLAS
         for _ in range(reps):
             t0 = time.perf_counter()
@@ -207,15 +214,22 @@ def run_reference(args: argparse.Namespace, w: dict) -> None:
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------------
-def build_shard(w: dict, rank: int, device, storage: str = "fp32"):  # noqa: ANN001, ANN201
+def build_shard(w: dict, rank: int, device, storage: str = "fp32", data: str = "gaussian"):  # noqa: ANN001, ANN201
     """Synthetic unit-norm corpus shard generated on the device (seeded per rank); float32, or rounded
-    to float16 (what RAGLite stores, _embed.py:140) for the fp16 layout."""
+    to float16 (what RAGLite stores, _embed.py:140) for the fp16 layout.  ``clustered``: tight clusters of
+    near-duplicates + low-rank background (tests/synth.py), float16-rounded values in either storage."""
     import torch
 
     n_rows = w["chunks"] * w["vecs"]
+    dtype = torch.float16 if storage == "fp16" else torch.float32
+    if data == "clustered":
+        from synth_torch import clustered_corpus_torch
+
+        E, _ = clustered_corpus_torch(n_rows, w["dim"], seed=1234 + rank, device=device, dtype=dtype)
+        return E
     g = torch.Generator(device=device)
     g.manual_seed(1234 + rank)
-    E = torch.empty((n_rows, w["dim"]), dtype=torch.float16 if storage == "fp16" else torch.float32, device=device)
+    E = torch.empty((n_rows, w["dim"]), dtype=dtype, device=device)
     step = 1 << 20
     for r0 in range(0, n_rows, step):
         r1 = min(n_rows, r0 + step)
@@ -327,11 +341,210 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
         dist.barrier(); dist.destroy_process_group()
 
 
+def oracle_check(local, index, Q_raw, adapter, ids, sims, counts, *, w: dict, n_check: int, world: int, rank: int,  # noqa: ANN001, PLR0913
+                 exact_maxsim: bool) -> dict:
+    """Correctness gate outside the timed region, at every N: ``n_check`` queries against the ORACLE
+    (``oracle.vector_search.vector_search_sql``, float64 distances, FLOAT ties -- the restatement of
+    _search.py:65-79,143-153) over the whole sharded corpus.
+
+    The oracle cannot hold a 61 GB shard per rank on the host, so every rank first shortlists, with a plain
+    float32 matmul on its device, the ``take`` = selection size + 64 rows of its shard nearest to each query
+    (a superset of that shard's share of the true selection unless more than 64 rows tie with the cut to
+    within float32 rounding), the shortlisted rows (vectors, global chunk ids, global row order) are
+    all-gathered, and rank 0 runs the oracle on that gathered table exactly as on any other table."""
+    import torch
+    import torch.distributed as dist
+
+    from oracle import vector_search as ovs   # checker only: never on the timed / product path
+
+    n = min(n_check, int(Q_raw.shape[0]))
+    k, num_hits, V = w["k"], w["num_hits"], w["vecs"]
+    sel = num_hits if num_hits else (k - 1) * V + 1
+    take = min(local.n_rows, sel + 64)
+    Qa = local.apply_adapter(Q_raw[:n].contiguous(), round_fp16=False) if adapter is not None else Q_raw[:n]
+    Qn = Qa / Qa.norm(dim=1, keepdim=True)
+    best_v = torch.full((n, take), -float("inf"), device=local.device)
+    best_r = torch.zeros((n, take), dtype=torch.int64, device=local.device)
+    step = 1 << 20
+    for r0 in range(0, local.n_rows, step):
+        blk = local.E[r0:r0 + step].float()
+        s = (Qn @ blk.T) * local.inv_norm[r0:r0 + step][None, :]
+        v, i = torch.topk(s, min(take, s.shape[1]), dim=1)
+        cv, ci = torch.cat([best_v, v], 1), torch.cat([best_r, i + r0], 1)
+        best_v, o = torch.topk(cv, take, dim=1)
+        best_r = torch.gather(ci, 1, o)
+    rows = best_r.reshape(-1)
+    Esel = local.E[rows].float().reshape(n, take, -1)
+    chunk = (local.row_chunk[rows].to(torch.int64) + local.chunk_base).reshape(n, take)
+    order = (best_r + (rank << 40)).reshape(n, take)
+    if world > 1:
+        def gather(t):  # noqa: ANN001, ANN202
+            out = torch.empty((world, *t.shape), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.contiguous())
+            return out
+        Esel, chunk, order = gather(Esel), gather(chunk), gather(order)
+        Esel = Esel.permute(1, 0, 2, 3).reshape(n, world * take, -1)
+        chunk = chunk.permute(1, 0, 2).reshape(n, world * take)
+        order = order.permute(1, 0, 2).reshape(n, world * take)
+    if rank != 0:
+        return {"checked_queries": n}
+    Esel, chunk, order, Qh = Esel.cpu().numpy(), chunk.cpu().numpy(), order.cpu().numpy(), Q_raw[:n].cpu().numpy()
+    exact_sets, exact_order, sim_err = 0, 0, 0.0
+    for b in range(n):
+        o = np.argsort(order[b], kind="stable")          # the gathered table in global row order
+        Eb, cb = Esel[b][o], chunk[b][o]
+        if exact_maxsim:
+            dist64 = ovs.vector_distances_f64(Eb, ovs.apply_query_adapter(adapter, Qh[b]), "cosine")
+            oo = np.argsort(dist64, kind="stable")
+            ref_ids, ref_s = ovs.group_hits(dist64[oo], cb[oo], k)
+        else:
+            ref_ids, ref_s, _ = ovs.vector_search_sql(Eb, None, Qh[b], num_results=k, oversample=w["oversample"], metric="cosine",
+                                                      adapter=adapter, f64=True, f32_ties=True, row_chunk=cb)
+        m = int(counts[b])
+        got = ids[b, :m]
+        exact_sets += int(m == len(ref_ids) and set(got.tolist()) == set(ref_ids.tolist()))
+        exact_order += int(got.tolist() == ref_ids.tolist())
+        mm = min(m, len(ref_s))
+        sim_err = max(sim_err, float(np.abs(sims[b, :mm] - np.asarray(ref_s[:mm], np.float64)).max()) if mm else 0.0)
+    return {"checked_queries": n, "identical_topk_sets": exact_sets, "identical_order": exact_order, "max_abs_score_err": sim_err,
+            "oracle": "oracle.vector_search.vector_search_sql(f64, FLOAT ties) over the gathered per-shard shortlists",
+            "shortlist_rows_per_shard": take}
+
+
+def run_pool(args: argparse.Namespace, w: dict) -> None:
+    """the late-chunking pool (_embed.py:119-140).  A "step" pools ``batch`` segments of 496
+    token rows x d float32 (bge-m3 at n_ctx 512, _embed.py:99) into per-sentence mean / L2 / fp16 rows in
+    ONE launch of ``rl_segment_mean_pool``; the token matrices stay on the device for ``value`` and come
+    from pinned host memory for ``e2e``."""
+    import torch
+
+    from raglite_b200 import _embed
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:      # the pool does not shard a document: replicas only; rank 0 reports
+        return
+    T_seg, d, n_seg = 496, w["dim"], w["batch"]
+    rng = np.random.default_rng(0)
+    seg_tokens, begins, ends, n_pre = [], [], [], []
+    base = 0
+    for _ in range(n_seg):          # ~24-token sentences; the first ~38% of a segment is preamble (not pooled)
+        toks = np.maximum(rng.poisson(24, size=32), 1)
+        toks = toks[: max(2, int(np.searchsorted(np.cumsum(toks), T_seg)))]
+        sizes = _embed.largest_remainder_sizes(T_seg, toks)
+        cuts = np.concatenate([[0], np.cumsum(sizes)]) + base
+        first = int(np.searchsorted(np.cumsum(toks), 0.382 * T_seg))
+        begins.append(cuts[first:-1]); ends.append(cuts[first + 1:])
+        seg_tokens.append(toks); n_pre.append(first); base += T_seg
+    rb, re_ = np.concatenate(begins), np.concatenate(ends)
+    S, T = len(rb), n_seg * T_seg
+    if args.impl == "reference":
+        from oracle import pool as opool     # CPU arm: the NumPy restatement (pinned to the reference's goldens)
+
+        n = 64
+        X = rng.standard_normal((n * T_seg, d)).astype(np.float32)
+        mats = [X[i * T_seg:(i + 1) * T_seg].astype(np.float64) for i in range(n)]
+        t0 = time.perf_counter()
+        reps = max(1, args.steps)
+        for _ in range(reps):
+            for i, m in enumerate(mats):
+                opool.late_chunk_pool([m], seg_tokens[i], [(0, n_pre[i], len(seg_tokens[i]))])
+        dt = (time.perf_counter() - t0) / reps
+        v = n * T_seg / dt
+        print(json.dumps({"impl": "reference", "metric": "late-chunking pool token rows/sec", "value": v, "unit": "token rows/s",
+                          "n_gpus": args.gpus, "steps": reps, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": w["desc"]},
+                          "cpu_baseline": {"value": v, "unit": "token rows/s", "cores": 1, "kind": "port",
+                                           "sample": f"{n} segments x {T_seg} x {d} (oracle.pool.late_chunk_pool, NumPy float64)"},
+                          "e2e": {"value": v, "unit": "token rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dev = torch.device("cuda")
+    X = torch.randn((T, d), device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    X_host = torch.empty((T, d), dtype=torch.float32, pin_memory=True)
+    X_host.copy_(X)
+    sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        out = _embed.segment_mean_pool(X, rb, re_, normalize=1)
+    torch.cuda.synchronize(); sampler.wait_first_sample()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    # row ranges live on the device for the timed region (what pool_segments uploads once per document)
+    rbd, red = torch.from_numpy(rb.astype(np.int32)).to(dev), torch.from_numpy(re_.astype(np.int32)).to(dev)
+    outd = torch.empty((S, d), dtype=torch.float16, device=dev)
+    from raglite_b200 import _lib
+    lib = _lib.load()
+    ev0.record()
+    for _ in range(args.steps):
+        _lib.check(lib.rl_segment_mean_pool(X.data_ptr(), d, d, rbd.data_ptr(), red.data_ptr(), S, 1, outd.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "rl_segment_mean_pool")
+    ev1.record(); torch.cuda.synchronize()
+    windows = [(w0, time.perf_counter())]
+    ms = ev0.elapsed_time(ev1) / args.steps
+    pooled_rows = int((re_ - rb).sum())
+    alg_bytes = pooled_rows * d * 4 + S * d * 2 + S * 8
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Xd = X_host.to(dev, non_blocking=True)
+        o = _embed.segment_mean_pool(Xd, rb, re_, normalize=1)
+        oh = o.cpu()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    windows.append((t0, time.perf_counter()))
+    clocks = sampler.stop(windows)
+    # parity of the timed configuration against the oracle on a few segments
+    from oracle import pool as opool
+    got = outd.cpu().numpy()
+    ulp_max, pos = 0, 0
+    for i in range(4):
+        ns = len(begins[i])
+        want = opool.late_chunk_pool([X_host[i * T_seg:(i + 1) * T_seg].numpy().astype(np.float64)], seg_tokens[i],
+                                     [(0, n_pre[i], len(seg_tokens[i]))])
+        ulp = np.abs(got[pos:pos + ns].view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+        ulp_max = max(ulp_max, int(ulp.max())); pos += ns
+    assert ulp_max <= 1, ulp_max
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    line = {"metric": "late-chunking pool token rows/sec", "value": T / (ms * 1e-3), "unit": "token rows/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "replicas only",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "segments": n_seg, "token_rows": T, "pooled_rows": pooled_rows, "sentences": S, "dim": d,
+                       "l2": "token matrix (%.1f GB) >> L2" % (T * d * 4 / 1e9)},
+            "e2e": {"value": T / (e2e_ms * 1e-3), "unit": "token rows/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(T * d * 4),
+                    "d2h_bytes_per_step": int(S * d * 2), "api": "raglite_b200._embed.segment_mean_pool (pinned host matrix in, host fp16 out)"},
+            "gpu_launches": args.steps, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                                     "traffic": None, "kernel": "segment_mean_pool_kernel", "kernel_ms": ms,
+                                                     "algorithmic_bytes": alg_bytes,
+                                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "clocks": clocks, "check": {"segments": 4, "max_fp16_ulp": ulp_max}}
+    if not args.no_cpu_baseline:
+        n = 32
+        t1 = time.perf_counter()
+        for i in range(n):
+            opool.late_chunk_pool([X_host[i * T_seg:(i + 1) * T_seg].numpy().astype(np.float64)], seg_tokens[i],
+                                  [(0, n_pre[i], len(seg_tokens[i]))])
+        cdt = time.perf_counter() - t1
+        line["cpu_baseline"] = {"value": n * T_seg / cdt, "unit": "token rows/s", "cores": 1, "kind": "port",
+                                "sample": f"{n} segments x {T_seg} x {d} (oracle.pool.late_chunk_pool, NumPy float64, 1 thread of pooling)"}
+    sys.stdout.flush(); os.dup2(saved, 1); print(json.dumps(line), flush=True); os.dup2(2, 1)
+    _ = world
+
+
 def main() -> None:  # noqa: PLR0915
     args = parse_args()
     w = resolve(args)
+    w["oversample"] = args.oversample
     if w["name"] == "c5":
         run_rerank(args, w)
+        return
+    if w["name"] == "pool":
+        run_pool(args, w)
         return
     if args.impl == "reference":
         run_reference(args, w)
@@ -358,9 +571,12 @@ def main() -> None:  # noqa: PLR0915
         dist.init_process_group("nccl", device_id=device)
 
     B, k, num_hits, d = w["batch"], w["k"], w["num_hits"], w["dim"]
-    E = build_shard(w, rank, device, args.storage)
+    E = build_shard(w, rank, device, args.storage, args.data)
     chunk_off = np.arange(0, E.shape[0] + 1, w["vecs"], dtype=np.int64)
-    local = rl.CorpusIndex(E, chunk_off, chunk_base=rank * w["chunks"], device=device, storage=args.storage)
+    meta = None
+    if args.filtered:   # two tags per chunk: "half" matches every other chunk (> 100k rows: rank-then-filter), "rare" 1 in 512
+        meta = [{"half": c & 1, "rare": int(c % 512 == 0)} for c in range(w["chunks"])]
+    local = rl.CorpusIndex(E, chunk_off, chunk_base=rank * w["chunks"], device=device, storage=args.storage, chunk_metadata=meta)
     esize = 2 if args.storage == "fp16" else 4
     del E
     index = ShardedIndex(local, group=dist.group.WORLD if world > 1 else None)
@@ -382,14 +598,16 @@ def main() -> None:  # noqa: PLR0915
     norm = total_chunks / TEN_M
 
     use_adapter = args.adapter == "on" or (args.adapter == "auto" and w["name"] == "c3")
+    A_np = None
     if use_adapter:  # orthogonal d x d float64 adapter as the cosine fit produces (_query_adapter.py:204-205)
         Ad = torch.linalg.svd(torch.randn((d, d), dtype=torch.float64, generator=torch.Generator().manual_seed(2)))
-        local.set_query_adapter((Ad[0] @ Ad[2]).numpy())
+        A_np = (Ad[0] @ Ad[2]).numpy()
+        local.set_query_adapter(A_np)
 
     def device_step(flags: int = 0):  # noqa: ANN202
         Qa = local.apply_adapter(Qd, round_fp16=False) if use_adapter else Qd     # _search.py:58-62
-        return index.search_device(Qa, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, checked=False, flags=flags,
-                                   sample_stride=args.sample_stride)
+        return index.search_pipeline(Qa, k=k, num_hits=num_hits, metric="cosine", algo=args.algo, flags=flags,
+                                     sample_stride=args.sample_stride)
 
     def barrier() -> None:
         if world > 1:
@@ -402,11 +620,10 @@ def main() -> None:  # noqa: PLR0915
     for _ in range(max(args.warmup, 3)):
         out = device_step()
     barrier()
-    status = index.last_status.cpu().numpy()
-    assert not (status & 1).any(), "candidate overflow in the timed configuration"
+    status = out[3].cpu().numpy()
+    overflow_in_timed_config = bool((status & 1).any())
     sampler.wait_first_sample()
     windows = []
-    stage_ms = {"prep": 0.0, "sample_scan": 0.0, "select": 0.0, "main_scan": 0.0, "finalize": 0.0}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     w0 = time.perf_counter()
@@ -424,23 +641,23 @@ def main() -> None:  # noqa: PLR0915
     # Stage times averaged over the timed steps themselves (CUDA events recorded on the launch stream
     # inside rl_maxsim_topk; the library keeps a ring of 32 event sets, read after the loop).
     stage_ms = local.kernel_times_ms()
-    last_stage = dict(stage_ms)
     stats = local.scan_stats()
     n_rows = local.n_rows
     scan_ms = float(stage_ms["main_scan"])
     comm_ms = None
     if world > 1:   # where does the multi-GPU step go: scan pipeline vs all-gather vs merge (CUDA events, this rank)
-        from raglite_b200._dist import gather_hits
-        from raglite_b200._index import merge_hits
+        from raglite_b200._index import merge_packed
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         acc = np.zeros(3)
+        H = num_hits if num_hits else k
         for _ in range(5):
             evs[0].record()
             res = local.scan(Qd, k=k, num_hits=num_hits, metric="cosine", algo=args.algo)
             evs[1].record()
-            g = gather_hits(res.hit_sim, res.hit_chunk, res.hit_count, index.group)
+            allb = torch.empty(world * res.packed.numel(), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allb, res.packed)
             evs[2].record()
-            merge_hits(*g, num_hits=num_hits, k=k)
+            merge_packed(allb, world, B, H, num_hits=num_hits, k=k)
             evs[3].record()
             torch.cuda.synchronize()
             acc += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(3)]) / 5
@@ -448,6 +665,7 @@ def main() -> None:  # noqa: PLR0915
     S = max(1, stats["sample_stride"])
     n_blocks = (n_rows + 127) // 128
     main_rows = min(n_rows, (n_blocks - (n_blocks + S - 1) // S) * 128)
+    groups = (B + 255) // 256
     alg_bytes = main_rows * d * esize + main_rows * 4 + B * d * 4    # corpus rows once + inv_norm + queries
     peaks = {}
     try:
@@ -457,77 +675,71 @@ def main() -> None:  # noqa: PLR0915
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        tr = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(w["name"])
-        if (tr and w["chunks"] == WORKLOADS[w["name"]]["chunks"] and B == WORKLOADS[w["name"]]["batch"]
-                and not args.exact_maxsim and args.storage == "fp32"):
-            traffic = tr["traffic_bytes_per_launch"]
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            f = ROOT / "profiles" / name
+            if not f.exists():
+                continue
+            tr = json.loads(f.read_text()).get(w["name"])
+            if (tr and w["chunks"] == WORKLOADS[w["name"]]["chunks"] and B == WORKLOADS[w["name"]]["batch"]
+                    and not args.exact_maxsim and args.storage == "fp32" and args.data == "gaussian"):
+                traffic = tr["traffic_bytes_per_launch"]
+                break
     except Exception:  # noqa: BLE001
         pass
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     flops = 2.0 * B * main_rows * d
+    tensor_peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "kernel": "main scan (emit mode), algo=%s" % {1: "fp32", 2: "tcgen05"}.get(stats["algo"], "?"),
-                "kernel_ms": scan_ms, "algorithmic_bytes": alg_bytes,
+                "kernel_ms": scan_ms, "algorithmic_bytes": alg_bytes, "query_groups_per_launch": groups,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "tensor_tflops": flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0,
-                "tensor_peak_tflops": peaks.get("bf16_tflops")}
+                "tensor_peak_tflops": tensor_peak,
+                "tensor_frac": (flops / (scan_ms * 1e-3) / 1e12 / tensor_peak) if (tensor_peak and scan_ms > 0) else None}
+    if B > 256 and tensor_peak:   # configs[2]: 2*B*d flop per 4*d bytes of corpus is past the ridge -> tensor pipe binds
+        roofline.update({"bound": "tensor", "achieved": roofline["tensor_tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
+                         "frac": roofline["tensor_frac"], "hbm_gbs": achieved, "hbm_frac": achieved / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"})
 
     # ---- end to end through the public API: host queries in, host results out, every step ----
     cfg = rl.RAGLiteConfig(db_url=f"bench://rank{rank}", reranker=None, vector_search_query_adapter=use_adapter)
     rl.register_index(cfg, index)
-    Q_np = Q_host.numpy()
-    for _ in range(2):
-        ids, sims, counts = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
-                                                   exact_maxsim=args.exact_maxsim, algo=args.algo)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ids, sims, counts = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
-                                                   exact_maxsim=args.exact_maxsim, algo=args.algo)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    windows.append((t0, t0 + e2e_s))
+
+    def timed_e2e(**kw):  # noqa: ANN003, ANN202
+        for _ in range(2):
+            r = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
+                                       exact_maxsim=args.exact_maxsim, algo=args.algo, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
+                                       exact_maxsim=args.exact_maxsim, algo=args.algo, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        windows.append((t0, t0 + dt))
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return r, float(tt.item()) * 1e3 / args.steps
+
+    (ids, sims, counts), e2e_ms = timed_e2e()
+    e2e_value = B / (e2e_ms * 1e-3) * norm
+    filtered = None
+    if args.filtered:   # both reference branches (_search.py:96-143), same batch, same API
+        _, ms_rare = timed_e2e(metadata_filter={"rare": 1})      # <= 100k matching rows: filter, then rank
+        _, ms_half = timed_e2e(metadata_filter={"half": 1})      # > 100k rows in a > 1M-vector table: rank, then filter
+        filtered = {"filter_first_ms": ms_rare, "rank_then_filter_ms": ms_half, "unfiltered_ms": e2e_ms,
+                    "filter_first_vs_unfiltered": ms_rare / e2e_ms, "rank_then_filter_vs_unfiltered": ms_half / e2e_ms}
     clocks = sampler.stop(windows)
     clocks["windows"] = "timed device steps + timed e2e steps"
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) * 1e3 / args.steps
-    e2e_value = B / (e2e_ms * 1e-3) * norm
 
-    # ---- correctness gate outside the timed region: a few queries against a float64 torch scan of the shard ----
+    # ---- correctness gate outside the timed region, at every N: the oracle over the whole sharded corpus ----
     check = {"checked_queries": 0}
-    if not args.no_check and world == 1:
-        nq = 4
-        exact = 0
-        sim_err = 0.0
-        Qc = local.apply_adapter(Qd, round_fp16=False) if use_adapter else Qd
-        for b in range(nq):
-            # fp32 matmul shortlists rows block by block; the shortlist is re-scored in float64.
-            take = max(num_hits, k * w["vecs"]) + 64
-            short = []
-            stepr = 1 << 21
-            for r0 in range(0, n_rows, stepr):
-                s = (local.E[r0:r0 + stepr].float() @ Qc[b]) * local.inv_norm[r0:r0 + stepr]
-                short.append(torch.topk(s, min(take, s.numel())).indices + r0)
-            rows_c = torch.cat(short)
-            e64 = local.E[rows_c].double()
-            s64 = (e64 @ Qc[b].double()) / (e64.norm(dim=1) * Qc[b].double().norm())
-            o = torch.argsort(s64, descending=True, stable=True)
-            if num_hits:
-                o = o[:num_hits]
-            rows_h, sims_h = rows_c[o].cpu().numpy(), s64[o].cpu().numpy()
-            ch = rows_h // w["vecs"]
-            uniq, first = np.unique(ch, return_index=True)
-            order = np.lexsort((uniq, -sims_h[first]))[:k]
-            ref_ids, ref_s = uniq[order], sims_h[first][order]
-            n = int(counts[b])
-            got = ids[b, :n] - local.chunk_base
-            exact += int(n == len(ref_ids) and set(got.tolist()) == set(ref_ids.tolist()))
-            m = min(n, len(ref_s))
-            sim_err = max(sim_err, float(np.abs(sims[b, :m] - ref_s[:m]).max()) if m else 0.0)
-        check = {"checked_queries": nq, "identical_topk_sets": exact, "max_abs_score_err": sim_err}
-        assert exact == nq and sim_err < 1e-4, check
+    if not args.no_check:
+        check = oracle_check(local, index, Qd, A_np, ids, sims, counts, w=w, n_check=args.check_queries, world=world, rank=rank,
+                             exact_maxsim=args.exact_maxsim)
+        if rank == 0 and args.data == "gaussian":
+            assert check["identical_topk_sets"] == check["checked_queries"] and check["max_abs_score_err"] < 1e-4, check
 
     if rank == 0:
         qps_raw = B / (ms_per_step * 1e-3)
@@ -535,24 +747,28 @@ def main() -> None:  # noqa: PLR0915
             "metric": "queries/sec multi-vector MaxSim over 10M chunks", "value": qps_raw * norm,
             "unit": "queries/s (10M-chunk equivalent)", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.storage == "fp32" else "f16", "data": "synthetic",
+            "dtype": "f32" if args.storage == "fp32" else "f16", "data": "synthetic" if args.data == "gaussian" else "synthetic (clustered)",
             "config": {"workload": w["desc"], "chunks_per_gpu": w["chunks"], "vecs_per_chunk": w["vecs"], "dim": d,
                        "batch": B, "k": k, "num_hits": num_hits, "metric": "cosine", "query_adapter": use_adapter,
-                       "corpus_storage": args.storage,
+                       "corpus_storage": args.storage, "corpus_data": args.data,
                        "semantics": "exact MaxSim" if args.exact_maxsim else "reference SQL (top-num_hits vectors -> group max -> top-k)",
                        "chunks_scanned": total_chunks, "normalisation": "value = batch / t_step * chunks_scanned / 10M",
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of per-shard hits" if world > 1 else "single GPU shard",
                        "l2": "corpus shard (%.1f GB) >> L2, no flush needed" % (n_rows * d * esize / 1e9)},
             "queries_per_sec_raw": qps_raw,
             "e2e": {"value": e2e_value, "unit": "queries/s (10M-chunk equivalent)", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4),
-                    "api": "raglite_b200.vector_search_batch (host numpy in -> host numpy out)"},
+                    "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4 + 4),
+                    "api": "raglite_b200.vector_search_batch (pinned host queries in -> host numpy out, one sync)"},
             "gpu_launches": int((stats["launches"] + 1 + (1 if use_adapter else 0)) * args.steps),
             "launches_per_step": {"scan_pipeline": stats["launches"], "merge": 1, "adapter_apply": 1 if use_adapter else 0},
             "roofline": roofline,
-            "stage_ms": stage_ms, "last_step_stage_ms": last_stage, "multi_gpu_stage_ms": comm_ms,
+            "stage_ms": stage_ms, "multi_gpu_stage_ms": comm_ms,
             "scan_stats": stats, "clocks": clocks, "check": check,
+            "robustness": {"fp32_fallback_queries": 0, "candidate_overflow_in_timed_config": overflow_in_timed_config,
+                           "streamed_survivor_queries": int(stats.get("survivors_max", 0) > 4096)},
         }
+        if filtered is not None:
+            line["filtered"] = filtered
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample_chunks or max(2048, min(w["chunks"], 16_384))
             r = cpu_reference_rate(w, sample, reps=3)

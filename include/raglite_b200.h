@@ -145,6 +145,7 @@ typedef struct rl_scan_stats {
   int64_t cand_total;
   int64_t cand_max;
   int64_t survivors_total;
+  int64_t survivors_max; /* largest per-query survivor count (> RL_MAX_SURVIVORS: that query took the streaming path) */
 } rl_scan_stats;
 int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream);
 
@@ -183,6 +184,15 @@ int rl_maxsim_copy_dump(const rl_scan_params* p, const void* workspace, float* d
 int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t* hit_count, int R,
                   int B, int H, int num_hits, int k, float* out_sim, int64_t* out_chunk,
                   int32_t* out_count, void* stream);
+
+/* Packed per-shard hit list, the unit the single all-gather of the sharded path moves (NCCL over NVLink):
+ *   chunk int64 [B, H] | sim float32 [B, H] | count int32 [B] | (status int32 [B])   -- padded to 16 bytes.
+ * rl_maxsim_topk can write straight into such a buffer (its four output pointers are the four sections),
+ * so nothing is re-packed before the collective, and rl_topk_merge_packed reads the R gathered buffers in
+ * place (rank_stride_bytes apart), so nothing is unpacked after it. */
+size_t rl_hits_packed_bytes(int B, int H, int with_status);
+int rl_topk_merge_packed(const void* packed, int64_t rank_stride_bytes, int R, int B, int H, int num_hits, int k,
+                         float* out_sim, int64_t* out_chunk, int32_t* out_count, void* stream);
 
 /* ---- Late-chunking pool: _embed.py:129-140 (and the simple pool :154-164) ---------------------
  * X[T,d] token embeddings (float32, row stride ld); sentence s averages rows

@@ -95,6 +95,8 @@ def vector_search_sql(  # noqa: PLR0913
     f64: bool = False,
     filter_first_max: int = 100_000,
     rank_first_limit: int = 1_000_000,
+    row_chunk: np.ndarray | None = None,
+    f32_ties: bool = False,
 ) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     """Exact-scan restatement of ``vector_search`` (``_search.py:58-153``, no HNSW approximation).
 
@@ -103,7 +105,10 @@ def vector_search_sql(  # noqa: PLR0913
     ``allowed_chunks`` (bool ``[C]``) restates the filter-first metadata branch
     (``_search.py:105-121``) when at most ``filter_first_max`` rows match, and the rank-then-filter
     branch (``_search.py:122-143``: the ``rank_first_limit`` nearest rows, then the filter) otherwise.
-    Ties are broken by row / chunk index (SQL leaves them unspecified).
+    Ties are broken by row / chunk index (SQL leaves them unspecified).  ``row_chunk`` (int64 ``[N]``)
+    names the owner chunk of every row directly instead of through ``chunk_off`` (a gathered subset of a
+    larger table).  ``f32_ties`` (with ``f64``) rounds the float64 distance to the FLOAT DuckDB returns
+    before ordering, so rows that tie in float32 are ordered by row index.
 
     Returns ``(chunk_index[int64], sim[float], hit_rows[int64])`` where ``hit_rows`` are the
     ``num_hits`` selected vector rows in ascending-distance order.
@@ -114,7 +119,9 @@ def vector_search_sql(  # noqa: PLR0913
     q = apply_query_adapter(adapter, q)
     num_hits = num_hits_rule(num_results, oversample, chunk_max_size)
     dist = (vector_distances_f64 if f64 else vector_distances)(E, q, metric)
-    r2c = row_to_chunk(chunk_off, E.shape[0])
+    if f64 and f32_ties:
+        dist = float_distance_of_f64(dist, metric)
+    r2c = row_to_chunk(chunk_off, E.shape[0]) if row_chunk is None else np.asarray(row_chunk, dtype=np.int64)
     rows = np.arange(E.shape[0])
     if allowed_chunks is not None:
         row_ok = np.asarray(allowed_chunks, dtype=bool)[r2c]
@@ -124,15 +131,87 @@ def vector_search_sql(  # noqa: PLR0913
             nearest = np.argsort(dist, kind="stable")[:rank_first_limit]
             rows = np.sort(nearest[row_ok[nearest]])
     order = rows[np.argsort(dist[rows], kind="stable")][:num_hits]
-    one = 1.0 if f64 else np.float32(1.0)
-    sim = one - dist[order]
-    hit_chunks = r2c[order]
-    # GROUP BY chunk_id -> max(sim): hits are in descending-sim order so the first occurrence of a
-    # chunk carries its max.
-    uniq, first = np.unique(hit_chunks, return_index=True)
+    ids, sims = group_hits(dist[order], r2c[order], num_results)
+    return ids, sims, order.astype(np.int64)
+
+
+def float_distance_of_f64(dist64: np.ndarray, metric: str) -> np.ndarray:
+    """The FLOAT a float64-accurate distance becomes when returned as DuckDB's ``FLOAT`` column:
+    cosine ``1 - s`` is formed in float32 from the float32-rounded similarity."""
+    if metric == "cosine":
+        return (np.float32(1.0) - (1.0 - dist64).astype(np.float32)).astype(np.float32)
+    return dist64.astype(np.float32)
+
+
+def group_hits(hit_dist: np.ndarray, hit_chunk: np.ndarray, num_results: int) -> tuple[np.ndarray, np.ndarray]:
+    """``GROUP BY chunk_id -> max(sim) -> ORDER BY sim DESC LIMIT num_results`` (``_search.py:143-150``) over
+    the selected vectors, given in ascending-distance order: the first occurrence of a chunk carries
+    its max; chunk ties are broken by chunk index."""
+    one = np.float32(1.0) if hit_dist.dtype == np.float32 else 1.0
+    sim = one - hit_dist
+    uniq, first = np.unique(hit_chunk, return_index=True)
     grouped_sim = sim[first]
     rank = np.lexsort((uniq, -grouped_sim.astype(np.float64)))[:num_results]
-    return uniq[rank].astype(np.int64), grouped_sim[rank], order.astype(np.int64)
+    return uniq[rank].astype(np.int64), grouped_sim[rank]
+
+
+def topn_rows_blocked(blocks, Q: np.ndarray, n_keep: int, metric: str = "cosine", *, f32_ties: bool = False,
+                      row_ok=None) -> list[tuple[np.ndarray, np.ndarray]]:
+    """``ORDER BY dist LIMIT n_keep`` (``_search.py:75-79``) for a batch of queries over a table that is
+    handed over block by block: ``blocks`` yields ``(first_row, E_block float32 [n, d])`` in row order
+    (e.g. slices copied back from the device), so a corpus larger than host memory can be checked.
+    Distances are float64 (``vector_distances_f64`` semantics; with ``f32_ties`` rounded to the FLOAT
+    DuckDB returns before ordering); ties are broken by row index exactly as the unblocked restatement
+    does.  ``row_ok(first_row, n) -> bool[n]`` optionally restricts the rows (metadata filter).
+    Returns, per query, ``(rows int64, dist)`` ascending."""
+    Q64 = np.asarray(Q, dtype=np.float64)
+    B = Q64.shape[0]
+    qq = np.einsum("ij,ij->i", Q64, Q64)
+    keep_d: list[np.ndarray] = [np.zeros(0, np.float32 if f32_ties else np.float64) for _ in range(B)]
+    keep_r: list[np.ndarray] = [np.zeros(0, np.int64) for _ in range(B)]
+    for row0, Eb in blocks:
+        E64 = np.asarray(Eb, dtype=np.float64)
+        n = E64.shape[0]
+        if n == 0:
+            continue
+        G = E64 @ Q64.T                                   # [n, B]
+        if metric == "cosine":
+            ee = np.einsum("ij,ij->i", E64, E64)
+            D = 1.0 - np.clip(G / np.sqrt(ee[:, None] * qq[None, :]), -1.0, 1.0)
+        elif metric == "dot":
+            D = -G
+        elif metric == "l2":
+            ee = np.einsum("ij,ij->i", E64, E64)
+            D = np.sqrt(np.maximum(ee[:, None] + qq[None, :] - 2.0 * G, 0.0))
+            # the unblocked restatement sums (e - q)^2; recompute the few kept rows that way below
+        else:
+            raise ValueError(f"Unsupported metric: {metric}")
+        ok = None if row_ok is None else np.asarray(row_ok(row0, n), dtype=bool)
+        for b in range(B):
+            d = D[:, b]
+            idx = np.arange(n) if ok is None else np.nonzero(ok)[0]
+            d = d[idx]
+            if len(d) > n_keep:
+                v = np.partition(d, n_keep - 1)[n_keep - 1]
+                sel = d <= v
+                d, idx = d[sel], idx[sel]
+            if metric == "l2" and len(idx):
+                diff = E64[idx] - Q64[b][None, :]
+                d = np.sqrt(np.einsum("ij,ij->i", diff, diff))
+            if f32_ties:
+                d = float_distance_of_f64(d, metric)
+            cd = np.concatenate([keep_d[b], d])
+            cr = np.concatenate([keep_r[b], idx.astype(np.int64) + int(row0)])
+            if len(cd) > n_keep:
+                v = np.partition(cd, n_keep - 1)[n_keep - 1]
+                sel = cd <= v
+                cd, cr = cd[sel], cr[sel]
+            keep_d[b], keep_r[b] = cd, cr
+    out = []
+    for b in range(B):
+        o = np.lexsort((keep_r[b], keep_d[b]))[:n_keep]
+        out.append((keep_r[b][o], keep_d[b][o]))
+    return out
 
 
 def maxsim_scores(

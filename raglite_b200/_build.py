@@ -46,14 +46,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libraglite_b200.so")
     LIB_DIR.mkdir(exist_ok=True)
-    tmp = LIB_PATH.with_suffix(".so.tmp")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), *[str(s) for s in sources()]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
-    if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
-    tmp.replace(LIB_PATH)
+    # One process per GPU: every rank may find the library stale at the same moment.  An exclusive file
+    # lock serialises them (the first one builds, the others re-check and find it fresh), and the output
+    # goes to a per-process temporary that is renamed into place, so nobody ever loads a half-written .so.
+    import fcntl
+
+    with open(LIB_DIR / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB_PATH
+            tmp = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+            cmd = [nvcc, *NVCC_FLAGS, "-o", str(tmp), *[str(s) for s in sources()]]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
+            if proc.returncode != 0:
+                tmp.unlink(missing_ok=True)
+                raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+            if verbose:
+                print(proc.stderr)
+            tmp.replace(LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH

@@ -14,7 +14,7 @@ from typing import Any
 import torch
 import torch.distributed as dist
 
-from ._index import CorpusIndex, ScanResult, limit_hits_to_nearest, merge_hits
+from ._index import CorpusIndex, ScanResult, limit_hits_to_nearest, merge_hits, merge_packed
 
 
 def pack_hits(hit_sim: torch.Tensor, hit_chunk: torch.Tensor, hit_count: torch.Tensor,
@@ -154,6 +154,22 @@ class ShardedIndex:
         res: ScanResult = self.local.scan(Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=row_allowed,
                                           mask_has_tombstones=mask_has_tombstones, flags=flags, cand_cap=cand_cap,
                                           sample_stride=sample_stride)
+        B, H = int(res.hit_sim.shape[0]), int(res.hit_sim.shape[1])
+        if res.packed is not None and rank_first_limit is None and Q.is_cuda:
+            # The scan wrote its outputs into one packed buffer: all-gather it as is, merge the gathered
+            # copies in place -- no pack / unpack kernels around the collective.
+            R = self.world
+            if self.group is not None and R > 1:
+                allb = torch.empty(R * res.packed.numel(), dtype=torch.uint8, device=res.packed.device)
+                dist.all_gather_into_tensor(allb, res.packed, group=self.group)
+            else:
+                allb = res.packed
+            per = allb.numel() // R
+            off = B * H * 12 + B * 4
+            status = torch.as_strided(allb.view(torch.int32), (R, B), (per // 4, 1), off // 4)
+            self.last_status = status
+            out = merge_packed(allb, R, B, H, num_hits=num_hits, k=k)
+            return (*out, status)
         sim, chunk, count, status = gather_hits(res.hit_sim, res.hit_chunk, res.hit_count, self.group, res.status)
         self.last_status = status
         if rank_first_limit is not None:

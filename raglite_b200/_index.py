@@ -102,6 +102,19 @@ class ScanResult:
     status: torch.Tensor     # [B] int32
     num_hits: int
     k: int
+    packed: torch.Tensor | None = None   # the four tensors above are views of this uint8 buffer (rl_hits_packed_bytes layout)
+
+
+def new_scan_result(B: int, H: int, num_hits: int, k: int, device: Any) -> ScanResult:
+    """Scan outputs laid out as ONE packed buffer (chunk | sim | count | status): the all-gather of the sharded
+    path sends it as is and ``rl_topk_merge_packed`` reads the gathered copies in place."""
+    n = int(_lib.load().rl_hits_packed_bytes(B, H, 1))
+    buf = torch.empty(max(n, 16), dtype=torch.uint8, device=device)
+    n8, n4 = B * H * 8, B * H * 4
+    return ScanResult(
+        buf[n8:n8 + n4].view(torch.float32).reshape(B, H), buf[:n8].view(torch.int64).reshape(B, H),
+        buf[n8 + n4:n8 + n4 + B * 4].view(torch.int32), buf[n8 + n4 + B * 4:n8 + n4 + B * 8].view(torch.int32),
+        num_hits, k, buf)
 
 
 class CorpusIndex:
@@ -196,6 +209,44 @@ class CorpusIndex:
             raise ValueError("one chunk_id per embedding row is required")
         offsets, chunk_ids = csr_from_row_chunk_ids(ids)
         return cls(E, offsets, chunk_ids=chunk_ids, **kw)
+
+    @classmethod
+    def from_table_rows(cls, rows: Any, dialect: str, *, storage: str = "auto", **kw: Any) -> "CorpusIndex":
+        """Build the index from a ``chunk_embedding`` result set as the database driver returns it:
+        ``(chunk_id, embedding)`` tuples of ``SELECT chunk_id, embedding FROM chunk_embedding ORDER BY id``
+        with DuckDB ``FLOAT[d]`` lists (``dialect="duckdb"``, ``_typing.py:178-208``), PostgreSQL ``halfvec``
+        text (``"postgresql"``, ``_typing.py:145-175``) or ``np.save`` blobs (``"numpy"``, ``_typing.py:57-78``).
+        ``storage="auto"`` picks the lossless float16 layout when every value is float16-representable
+        -- always the case for rows RAGLite wrote (``_embed.py:140``) -- and float32 otherwise."""
+        from . import _rows
+
+        ids, E = _rows.table_rows(rows, dialect)
+        E, storage = cls._pick_storage(E, storage)
+        return cls.from_chunk_embedding_rows(ids, E, storage=storage, **kw)
+
+    def append_table_rows(self, rows: Any, dialect: str, **kw: Any) -> None:
+        """``append_chunk_embedding_rows`` for driver-shaped rows (one flush of ``insert_documents``,
+        ``_insert.py:247-255``)."""
+        from . import _rows
+
+        ids, E = _rows.table_rows(rows, dialect)
+        self.append_chunk_embedding_rows(ids, E, **kw)
+
+    @staticmethod
+    def _pick_storage(E: np.ndarray, storage: str) -> tuple[np.ndarray, str]:
+        from . import _rows
+
+        if storage != "auto":
+            return E, storage
+        d = int(E.shape[1]) if E.ndim == 2 else 0
+        h = _rows.lossless_float16(E) if d % 8 == 0 and E.size else None
+        if h is None:
+            return E.astype(np.float32, copy=False), "fp32"
+        # the cosine fast path of the float16 layout needs rows that are not tiny (norm >= 0.5)
+        nrm = np.linalg.norm(h.astype(np.float32), axis=1)
+        if nrm.size and (nrm.min() < 0.5 or np.abs(h).max() > 1024):
+            return E.astype(np.float32, copy=False), "fp32"
+        return h, "fp16"
 
     def _to_storage(self, E: torch.Tensor) -> torch.Tensor:
         """Rows in the index's storage dtype on its device.  ``fp16`` storage is lossless only: RAGLite's
@@ -554,11 +605,7 @@ class CorpusIndex:
                 raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
             ws = self._workspace(need)
             if out is None:
-                out = ScanResult(
-                    torch.empty((B, H), dtype=torch.float32, device=self.device),
-                    torch.empty((B, H), dtype=torch.int64, device=self.device),
-                    torch.empty((B,), dtype=torch.int32, device=self.device),
-                    torch.empty((B,), dtype=torch.int32, device=self.device), num_hits, k)
+                out = new_scan_result(B, H, num_hits, k, self.device)
             check(self.lib.rl_maxsim_topk(C.byref(p), _ptr(out.hit_sim), _ptr(out.hit_chunk), _ptr(out.hit_count),
                                           _ptr(out.status), _ptr(ws), ws.numel(), _stream()),
                   "rl_maxsim_topk")
@@ -746,6 +793,20 @@ def merge_hits(  # noqa: PLR0913
     with torch.cuda.device(dev):
         check(lib.rl_topk_merge(_ptr(hs), _ptr(hc), _ptr(hn), R, B, H, num_hits, k, _ptr(out_sim), _ptr(out_chunk),
                                 _ptr(out_count), _stream()), "rl_topk_merge")
+    return out_sim, out_chunk, out_count
+
+
+def merge_packed(packed: torch.Tensor, R: int, B: int, H: int, *, num_hits: int, k: int
+                 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``rl_topk_merge_packed`` over ``R`` gathered packed hit lists (``packed`` is the all-gather output)."""
+    lib = _lib.load()
+    dev = packed.device
+    out_sim = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_chunk = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.rl_topk_merge_packed(_ptr(packed), packed.numel() // R, R, B, H, num_hits, k, _ptr(out_sim), _ptr(out_chunk),
+                                       _ptr(out_count), _stream()), "rl_topk_merge_packed")
     return out_sim, out_chunk, out_count
 
 

@@ -22,7 +22,7 @@ RL_MAX_SURVIVORS = 4096   # finalize window (include/raglite_b200.h)
 
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
-    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_row_mask",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_topk_merge_packed", "rl_hits_packed_bytes", "rl_row_mask",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
@@ -44,7 +44,7 @@ class ScanStats(C.Structure):
     _fields_ = [
         ("launches", C.c_int32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32), ("algo", C.c_int32),
         ("n_sample_rows", C.c_int64), ("cand_total", C.c_int64), ("cand_max", C.c_int64),
-        ("survivors_total", C.c_int64),
+        ("survivors_total", C.c_int64), ("survivors_max", C.c_int64),
     ]
 
 
@@ -86,6 +86,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_row_mask.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.rl_maxsim_copy_dump.argtypes = [C.POINTER(ScanParams), vp, vp, C.POINTER(C.c_int64), vp]
     lib.rl_topk_merge.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.rl_hits_packed_bytes.argtypes = [i32, i32, i32]
+    lib.rl_hits_packed_bytes.restype = C.c_size_t
+    lib.rl_topk_merge_packed.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.rl_segment_mean_pool.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]
     lib.rl_xenc_linear_image_bytes.argtypes = [i32, i32]
     lib.rl_xenc_linear_image_bytes.restype = C.c_size_t
@@ -95,7 +98,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_xenc_workspace_bytes.restype = C.c_size_t
     lib.rl_xenc_score.argtypes = [C.POINTER(XencWeights), vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, C.c_size_t, vp]
     for name in EXPORTS:
-        if name not in ("rl_last_error", "rl_maxsim_workspace_bytes", "rl_xenc_linear_image_bytes", "rl_xenc_workspace_bytes"):
+        if name not in ("rl_last_error", "rl_maxsim_workspace_bytes", "rl_xenc_linear_image_bytes", "rl_xenc_workspace_bytes",
+                        "rl_hits_packed_bytes"):
             getattr(lib, name).restype = C.c_int
 
 

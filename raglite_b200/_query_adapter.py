@@ -34,15 +34,25 @@ def _optimize_query_target(q: np.ndarray, P: np.ndarray, N: np.ndarray, *, alpha
     return (q64 + D.T @ mu).astype(dtype)
 
 
-def _best_vectors(index: CorpusIndex, chunks: Sequence[int], q: np.ndarray) -> np.ndarray:
-    """Row ``argmax(E_c @ q)`` of every chunk in ``chunks`` (one gather + one matvec on the device)."""
-    off = index.chunk_off
-    rows = np.concatenate([np.arange(off[c], off[c + 1]) for c in chunks])
-    seg = np.cumsum([0] + [int(off[c + 1] - off[c]) for c in chunks])
-    E = index.E[torch.from_numpy(rows).to(index.device)].float()
-    s = (E @ torch.from_numpy(q.astype(np.float32)).to(index.device)).cpu().numpy()
-    best = [rows[seg[i] + int(np.argmax(s[seg[i]:seg[i + 1]]))] for i in range(len(chunks))]
-    return index.E[torch.from_numpy(np.asarray(best)).to(index.device)].float().cpu().numpy()
+def _best_vectors(index: Any, chunks: Sequence[int], q: np.ndarray) -> np.ndarray:
+    """Row ``argmax(E_c @ q)`` of every chunk in ``chunks`` (GLOBAL chunk indices, as ``vector_search_batch``
+    returns them): one gather + one matvec on the device.  On a sharded corpus every rank resolves the
+    chunks it owns and the rows are summed over the shards (each chunk lives on exactly one)."""
+    local: CorpusIndex = getattr(index, "local", index)
+    off, base = local.chunk_off, local.chunk_base
+    out = torch.zeros((len(chunks), local.d), dtype=torch.float32, device=local.device)
+    mine = [(i, int(c) - base) for i, c in enumerate(chunks) if base <= int(c) < base + local.n_chunks]
+    if mine:
+        rows = np.concatenate([np.arange(off[c], off[c + 1]) for _, c in mine])
+        seg = np.cumsum([0] + [int(off[c + 1] - off[c]) for _, c in mine])
+        E = local.E[torch.from_numpy(rows).to(local.device)].float()
+        s = (E @ torch.from_numpy(q.astype(np.float32)).to(local.device)).cpu().numpy()
+        best = [rows[seg[j] + int(np.argmax(s[seg[j]:seg[j + 1]]))] for j in range(len(mine))]
+        out[torch.tensor([i for i, _ in mine], device=local.device)] = \
+            local.E[torch.from_numpy(np.asarray(best)).to(local.device)].float()
+    elif not hasattr(index, "sum_over_shards") or getattr(index, "world", 1) == 1:
+        raise ValueError("retrieved chunks are not in this index (chunk_base mismatch)")
+    return index.sum_over_shards(out).cpu().numpy()
 
 
 def update_query_adapter(  # noqa: PLR0913
@@ -80,7 +90,7 @@ def update_query_adapter(  # noqa: PLR0913
         if not is_rel.any() or is_rel.all():
             continue
         q = np.ravel(q)
-        best = _best_vectors(local, retrieved, q)
+        best = _best_vectors(index, retrieved, q)
         t = _optimize_query_target(q, best[is_rel], best[~is_rel], alpha=optimize_gap)
         Qs.append(q.astype(np.float64))
         Ts.append(t.astype(np.float64))

@@ -72,8 +72,13 @@ class B200CrossEncoderRanker(ScoreFnRanker):
         if self._engine is None:
             from ._xenc import CrossEncoderEngine
 
-            self._engine = CrossEncoderEngine.from_pretrained(
-                (self.cache_dir / self.model_name) if self.cache_dir else Path(self.model_name),
-                max_length=self.max_length, device=self.device,
-            )
+            path = (self.cache_dir / self.model_name) if self.cache_dir else Path(self.model_name)
+            if not (path / "config.json").exists():
+                raise FileNotFoundError(
+                    f"B200CrossEncoderRanker: no Hugging Face model directory at {path}.  The reference's FlashRank "
+                    "reranker downloads an ONNX file on first use; this ranker needs the same model as HF weights "
+                    "(config.json + model.safetensors + tokenizer.json, e.g. `huggingface-cli download "
+                    f"cross-encoder/{self.model_name} --local-dir {path}`), or pass any object with a "
+                    ".rank(query=, docs=) method as RAGLiteConfig.reranker (None disables reranking).  See INTEGRATION.md.")
+            self._engine = CrossEncoderEngine.from_pretrained(path, max_length=self.max_length, device=self.device)
         return self._engine.score_pairs([query] * len(docs), list(docs))

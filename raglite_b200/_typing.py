@@ -10,6 +10,7 @@ import numpy as np
 if TYPE_CHECKING:
     from ._config import RAGLiteConfig
     from ._index import Chunk
+    from ._search import ChunkSpan
 
 ChunkId = str
 DocumentId = str
@@ -40,4 +41,4 @@ class SearchMethod(Protocol):
     def __call__(
         self, query: str, *, num_results: int, metadata_filter: MetadataFilter | None = None,
         config: "RAGLiteConfig | None" = None,
-    ) -> "tuple[list[ChunkId], list[float]] | list[Chunk]": ...
+    ) -> "tuple[list[ChunkId], list[float]] | list[Chunk] | list[ChunkSpan]": ...

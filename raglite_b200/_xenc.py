@@ -175,6 +175,14 @@ class CrossEncoderEngine:
         cu[1:] = np.cumsum(lens)
         flat_ids = np.concatenate(ids).astype(np.int32)
         flat_types = np.concatenate(type_ids).astype(np.int32)
+        # A tokenizer that does not match the weights would index past the embedding tables.
+        w = self.weights
+        if T and (int(flat_ids.min()) < 0 or int(flat_ids.max()) >= w.vocab):
+            raise ValueError(f"token id outside the model's vocabulary [0, {w.vocab}) -- tokenizer / weights mismatch?")
+        if T and (int(flat_types.min()) < 0 or int(flat_types.max()) >= w.type_vocab):
+            raise ValueError(f"token type id outside [0, {w.type_vocab})")
+        if P and int(lens.max()) > w.max_pos:
+            raise ValueError(f"sequence longer than the model's {w.max_pos} positions")
         flat_pos = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
         host = torch.from_numpy(np.concatenate([flat_ids, flat_types, flat_pos, cu]))
         dev = host.to(self.device, non_blocking=True)

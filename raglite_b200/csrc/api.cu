@@ -402,6 +402,7 @@ extern "C" int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, r
     out->cand_total += cnt[b];
     if (cnt[b] > out->cand_max) out->cand_max = cnt[b];
     out->survivors_total += cnt[p->B + b];
+    if (cnt[p->B + b] > out->survivors_max) out->survivors_max = cnt[p->B + b];
   }
   delete[] cnt;
   return RL_OK;
@@ -431,6 +432,31 @@ extern "C" int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, con
   MergeArgs m;
   m.hit_sim = hit_sim; m.hit_chunk = hit_chunk; m.hit_count = hit_count; m.out_sim = out_sim;
   m.out_chunk = out_chunk; m.out_count = out_count; m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k;
-  m.win = 0;
+  m.win = 0; m.sim_rs = 0; m.chunk_rs = 0; m.count_rs = 0;
+  return launch_merge(m, (cudaStream_t)stream);
+}
+
+extern "C" size_t rl_hits_packed_bytes(int B, int H, int with_status) {
+  if (B < 0 || H < 0) return 0;
+  const size_t raw = (size_t)B * H * 12 + (size_t)B * 4 * (with_status ? 2 : 1);
+  return (raw + 15) / 16 * 16;
+}
+
+extern "C" int rl_topk_merge_packed(const void* packed, int64_t rank_stride_bytes, int R, int B, int H, int num_hits, int k,
+                                    float* out_sim, int64_t* out_chunk, int32_t* out_count, void* stream) {
+  RL_REQUIRE(R >= 1 && B >= 0 && H >= 1 && k >= 1 && num_hits >= 0, RL_EINVAL, "rl_topk_merge_packed: bad sizes");
+  if (B == 0) return RL_OK;
+  RL_REQUIRE(packed && out_sim && out_chunk && out_count, RL_EINVAL, "rl_topk_merge_packed: null pointer");
+  RL_REQUIRE(rank_stride_bytes % 8 == 0 && (reinterpret_cast<uintptr_t>(packed) & 7) == 0 &&
+                 rank_stride_bytes >= (int64_t)B * H * 12 + (int64_t)B * 4,
+             RL_EINVAL, "rl_topk_merge_packed: rank stride must be a multiple of 8 covering one packed list");
+  const unsigned char* base = static_cast<const unsigned char*>(packed);
+  MergeArgs m;
+  m.hit_chunk = reinterpret_cast<const int64_t*>(base);
+  m.hit_sim = reinterpret_cast<const float*>(base + (size_t)B * H * 8);
+  m.hit_count = reinterpret_cast<const int32_t*>(base + (size_t)B * H * 12);
+  m.out_sim = out_sim; m.out_chunk = out_chunk; m.out_count = out_count;
+  m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k; m.win = 0;
+  m.chunk_rs = rank_stride_bytes / 8; m.sim_rs = rank_stride_bytes / 4; m.count_rs = rank_stride_bytes / 4;
   return launch_merge(m, (cudaStream_t)stream);
 }

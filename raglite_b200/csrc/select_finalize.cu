@@ -655,13 +655,16 @@ __global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
   const int b = blockIdx.x;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
+  const int64_t sim_rs = m.sim_rs ? m.sim_rs : (int64_t)m.B * m.H;
+  const int64_t chunk_rs = m.chunk_rs ? m.chunk_rs : (int64_t)m.B * m.H;
+  const int64_t count_rs = m.count_rs ? m.count_rs : (int64_t)m.B;
   for (int r = 0; r < m.R; ++r) {
-    const int cnt = min(m.hit_count[(size_t)r * m.B + b], m.H);
+    const int cnt = min(m.hit_count[(size_t)r * count_rs + b], m.H);
     __shared__ int base;
     if (threadIdx.x == 0) { base = s_n; s_n += cnt; }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const size_t e = ((size_t)r * m.B + b) * m.H + i;
+      const size_t e = (size_t)r * sim_rs + (size_t)b * m.H + i;
       keys[base + i] = ((uint64_t)(~f2ord(m.hit_sim[e])) << 32) | (uint32_t)(r * m.H + i);
     }
     __syncthreads();
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
   for (int i = threadIdx.x; i < n_keep; i += blockDim.x) {
     const uint32_t e = (uint32_t)keys[i];
     const int r = e / m.H, j = e % m.H;
-    chunk[i] = m.hit_chunk[((size_t)r * m.B + b) * m.H + j];
+    chunk[i] = m.hit_chunk[(size_t)r * chunk_rs + (size_t)b * m.H + j];
   }
   __syncthreads();
   first_occurrence(chunk, n_keep, flags);

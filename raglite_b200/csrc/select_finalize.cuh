@@ -46,6 +46,7 @@ struct MergeArgs {
   int32_t* out_count;         // [B]
   int32_t R, B, H, num_hits, k;
   int32_t win;                // set by launch_merge: power of two >= R * H
+  int64_t sim_rs, chunk_rs, count_rs;  // element strides between the ranks' lists (0 = contiguous [R, B, H] / [R, B])
 };
 
 constexpr int kFinalizeScratch = 20480;  // histogram (16 KB) / flags + positions (20 KB)

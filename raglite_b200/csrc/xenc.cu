@@ -337,13 +337,15 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* __restrict
                                                        const int32_t* __restrict__ pos_ids, const __half* __restrict__ word,
                                                        const __half* __restrict__ pos, const __half* __restrict__ type,
                                                        const float* __restrict__ g, const float* __restrict__ bta, float eps,
-                                                       int T, int H, __half* __restrict__ out) {
+                                                       int T, int H, int vocab, int max_pos, int type_vocab,
+                                                       __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= T) return;
-  const __half* w = word + (size_t)ids[tok] * H;
-  const __half* p = pos + (size_t)pos_ids[tok] * H;
-  const __half* ty = type + (size_t)type_ids[tok] * H;
+  // ids are validated on the host (_xenc.py); the clamp only keeps a bad caller from reading out of bounds
+  const __half* w = word + (size_t)min(max(ids[tok], 0), vocab - 1) * H;
+  const __half* p = pos + (size_t)min(max(pos_ids[tok], 0), max_pos - 1) * H;
+  const __half* ty = type + (size_t)min(max(type_ids[tok], 0), type_vocab - 1) * H;
   float x[16];  // H <= 512
   float s = 0.f;
 #pragma unroll
@@ -722,7 +724,7 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   embed_ln_kernel<<<tok_blocks, 256, 0, stream>>>(input_ids, type_ids, pos_ids, reinterpret_cast<const __half*>(w->word_emb),
                                                   reinterpret_cast<const __half*>(w->pos_emb),
                                                   reinterpret_cast<const __half*>(w->type_emb), w->emb_ln_g, w->emb_ln_b,
-                                                  w->ln_eps, T, H, hidden);
+                                                  w->ln_eps, T, H, w->vocab, w->max_pos, w->type_vocab, hidden);
   RL_CUDA_CHECK(cudaGetLastError());
   const size_t att_smem = (size_t)((max_len + 63) / 64 * 64) * kAttPitch * 2 * sizeof(__half);
   RL_REQUIRE(att_smem <= 200 * 1024, RL_EUNSUPPORTED, "rl_xenc_score: max_len=%d too long for the attention kernel", max_len);

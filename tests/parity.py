@@ -57,3 +57,35 @@ def check_exact_maxsim(E, chunk_off, q, got_ids, got_sims, *, k, metric="cosine"
     if gap > TIE_GAP and inner > TIE_GAP:
         assert got_ids.tolist() == ref_ids.tolist()
     assert np.allclose(np.sort(s[got_ids])[::-1], ref_s, atol=10 * TIE_GAP)
+
+
+def check_sql_from_topn(top_rows, top_dist, row_chunk, got_ids, got_sims, *, k, num_hits):
+    """Compare one query's result with the oracle's ``ORDER BY dist LIMIT`` list (``oracle.topn_rows_blocked``
+    with ``f32_ties=True``; at least ``num_hits + 1`` rows when the table has that many) through the
+    shared ``GROUP BY`` restatement.  Returns True for an exact match (ids, order, count); a mismatch is
+    only accepted when the cut or two neighbouring scores tie within ``TIE_GAP`` -- SQL leaves those
+    orders unspecified -- and then the score lists must still agree."""
+    top_rows, top_dist = np.asarray(top_rows), np.asarray(top_dist)
+    chunks = np.asarray(row_chunk)[top_rows] if not callable(row_chunk) else row_chunk(top_rows)
+    ref_ids, ref_sims = ovs.group_hits(top_dist[:num_hits], chunks[:num_hits], k)
+    got_ids = np.asarray(got_ids)
+    got_sims = np.asarray(got_sims, dtype=np.float64)
+    assert np.all(np.diff(got_sims) <= 1e-6), "scores must be descending"
+    if got_ids.tolist() == ref_ids.tolist():
+        assert np.allclose(got_sims, ref_sims, atol=SCORE_TOL), np.abs(got_sims - ref_sims).max()
+        return True
+    d64 = top_dist.astype(np.float64)
+    vec_gap = (d64[num_hits] - d64[num_hits - 1]) if len(d64) > num_hits else np.inf
+    sim_gaps = np.abs(np.diff(ref_sims.astype(np.float64))) if len(ref_sims) > 1 else np.array([np.inf])
+    assert vec_gap <= TIE_GAP or sim_gaps.min() <= TIE_GAP, ("mismatch without a tie", got_ids[:10], ref_ids[:10], vec_gap)
+    # every returned chunk must own one of the listed vectors and carry that vector's similarity
+    best = {}
+    for c, dd in zip(chunks.tolist(), d64.tolist()):
+        best.setdefault(c, 1.0 - dd)
+    assert all(int(c) in best for c in got_ids), "a returned chunk owns none of the nearest vectors"
+    assert np.allclose(got_sims, [best[int(c)] for c in got_ids], atol=SCORE_TOL)
+    n = min(len(got_ids), len(ref_ids))
+    if vec_gap > TIE_GAP:   # the vector set is unambiguous, only the order of tied chunks may differ
+        assert len(got_ids) == len(ref_ids) and sorted(got_ids.tolist()) == sorted(ref_ids.tolist())
+    assert np.allclose(got_sims[:n], ref_sims[:n], atol=SCORE_TOL)
+    return False

@@ -118,6 +118,73 @@ def _worker(rank: int, world: int, port: int, tmp: str) -> None:
         first_ids, _, _ = ovs.vector_search_sql(E, off, q, num_results=k, allowed_chunks=tagged, f64=True)
         changed += ref_ids.tolist() != first_ids.tolist()
     assert changed >= 1, "the cut must change at least query 0's answer"
+
+    # The status words ride along in the same all-gather (one collective per search).
+    st = torch.full((len(Q),), rank, dtype=torch.int32)
+    g4 = gather_hits(torch.from_numpy(sim), torch.from_numpy(chunk), torch.from_numpy(count), dist.group.WORLD, st)
+    assert len(g4) == 4 and g4[3].shape == (world, len(Q)) and g4[3][1].tolist() == [1] * len(Q)
+    assert torch.equal(g4[0], g_sim) and torch.equal(g4[1], g_chunk)
+
+    # dot metric, shards whose largest row norms differ -- the bisection bracket must be the
+    # same on every rank (max over shards), or the summed counts mix different thresholds.
+    scale = np.where(np.arange(len(E)) >= int(off[ranges[1][0]]), 3.0, 1.0).astype(np.float32)[:, None]
+    Ed = E * scale
+
+    class FakeDotShard:
+        storage = "fp32"
+        stats = torch.tensor([float(np.linalg.norm(Ed[int(off[lo]):int(off[hi])], axis=1).max()), 1.0, 1.0, 0.0])
+
+        def count_at_least(self, Qd, floor, **_):
+            r0, r1 = int(off[lo]), int(off[hi])
+            sims = [1.0 - ovs.vector_distances_f64(Ed[r0:r1], q, "dot") for q in Qd.numpy()]
+            return torch.tensor([int((s >= float(f)).sum()) for s, f in zip(sims, floor)], dtype=torch.int32)
+
+    def shard_hits_dot(allowed):
+        r0, r1 = int(off[lo]), int(off[hi])
+        r2c = ovs.row_to_chunk(off[lo:hi + 1] - r0, r1 - r0) + lo
+        sim_ = np.full((len(Q), num_hits), -np.inf, np.float32); ch_ = np.full((len(Q), num_hits), -1, np.int64)
+        cn_ = np.zeros(len(Q), np.int32)
+        for b, q in enumerate(Q):
+            d_ = ovs.vector_distances_f64(Ed[r0:r1], q, "dot")
+            rows_ = np.nonzero(allowed[r2c])[0]
+            o_ = rows_[np.argsort(d_[rows_], kind="stable")][:num_hits]
+            sim_[b, :len(o_)] = (1.0 - d_[o_]).astype(np.float32); ch_[b, :len(o_)] = r2c[o_]; cn_[b] = len(o_)
+        return sim_, ch_, cn_
+
+    sim, chunk, count = shard_hits_dot(tagged)
+    g_sim, g_chunk, g_count = gather_hits(torch.from_numpy(sim), torch.from_numpy(chunk), torch.from_numpy(count),
+                                          dist.group.WORLD)
+    sharded = ShardedIndex(FakeDotShard(), dist.group.WORLD)
+    kept = limit_hits_to_nearest(sharded, torch.from_numpy(Q), g_sim, g_count, k=k, num_hits=num_hits, metric="dot",
+                                 limit=limit)
+    both = [torch.zeros_like(kept) for _ in range(world)]
+    dist.all_gather(both, kept)
+    assert torch.equal(both[0], both[1]), "every rank must keep the same hits"
+    merged = merge_numpy(g_sim.numpy(), g_chunk.numpy(), kept.numpy(), num_hits, k)
+    for b, q in enumerate(Q):
+        ref_ids, ref_sims, _ = ovs.vector_search_sql(Ed, off, q, num_results=k, metric="dot", allowed_chunks=tagged, f64=True,
+                                                     filter_first_max=0, rank_first_limit=limit)
+        assert merged[b][0].tolist() == ref_ids.tolist(), (b, merged[b][0], ref_ids)
+
+    # shard ranges are gathered and checked; chunk ids resolve across ranks after refresh(chunk_ids=True).
+    class FakeLocal:
+        def __init__(self, base, n):
+            self.chunk_base, self.n_chunks, self.chunk_ids = base, n, [f"r{rank}-c{i}" for i in range(n)]
+
+    bases = ShardedIndex.shard_bases(world)
+    sh = ShardedIndex(FakeLocal(bases[rank], 5 + rank), dist.group.WORLD)
+    assert sh.ranges == [(bases[0], 5), (bases[1], 6)]
+    sh.refresh(chunk_ids=True)
+    assert sh.chunk_id_of(bases[1] + 3) == "r1-c3" and sh.chunk_id_of(2) == "r0-c2"
+    sh.check_local_growth(1000)                       # spaced bases: room to grow
+    with pytest.raises(ValueError, match="overlap"):
+        ShardedIndex(FakeLocal(0 if rank == 0 else 3, 5), dist.group.WORLD)
+    tight = ShardedIndex(FakeLocal(rank * 5, 5), dist.group.WORLD)
+    if rank == 0:
+        with pytest.raises(ValueError, match="next shard"):
+            tight.check_local_growth(6)
+    else:
+        tight.check_local_growth(6)                   # the last shard may grow
     dist.barrier()
     dist.destroy_process_group()
     Path(tmp, f"ok{rank}").write_text("ok")

@@ -98,3 +98,43 @@ def test_blas_batch_matches_loop():
         sq, ss, _ = ovs.vector_search_sql(E, off, q, num_results=10)
         n = len(sq)
         assert ids_h[b, :n].tolist() == sq.tolist() and np.allclose(sc_h[b, :n], ss, atol=1e-5)
+
+
+def test_blocked_oracle_equals_the_unblocked_restatement():
+    """``topn_rows_blocked`` (used for corpora that only exist on the device) is the same ORDER BY / LIMIT."""
+    for metric in ("cosine", "dot", "l2"):
+        E, off = make_corpus(400, (1, 7), 40, seed=3, normalize=(metric == "cosine"))
+        Q = make_queries(E, 5, seed=4)
+        r2c = ovs.row_to_chunk(off)
+        blocks = [(r0, E[r0:r0 + 257]) for r0 in range(0, len(E), 257)]
+        for f32 in (False, True):
+            top = ovs.topn_rows_blocked(blocks, Q, 80, metric, f32_ties=f32)
+            for b, q in enumerate(Q):
+                ids, sims, rows = ovs.vector_search_sql(E, off, q, num_results=20, metric=metric, f64=True, f32_ties=f32)
+                assert np.array_equal(rows, top[b][0])
+                i2, s2 = ovs.group_hits(top[b][1], r2c[top[b][0]], 20)
+                assert np.array_equal(ids, i2) and np.allclose(sims, s2, atol=1e-12)
+    # a gathered subset of a table: owners given per row
+    E, off = make_corpus(100, (1, 4), 16, seed=9)
+    q = make_queries(E, 1, seed=10)[0]
+    sub = np.sort(np.random.default_rng(0).choice(len(E), size=len(E) // 2, replace=False))
+    ids, sims, rows = ovs.vector_search_sql(E[sub], None, q, num_results=5, f64=True, row_chunk=ovs.row_to_chunk(off)[sub])
+    allowed_rows = np.zeros(len(E), bool); allowed_rows[sub] = True
+    dist = ovs.vector_distances_f64(E, q)
+    order = sub[np.argsort(dist[sub], kind="stable")][:40]
+    want_ids, want_sims = ovs.group_hits(dist[order], ovs.row_to_chunk(off)[order], 5)
+    assert np.array_equal(ids, want_ids) and np.allclose(sims, want_sims)
+
+
+def test_clustered_generator_has_massive_near_ties():
+    from synth import make_clustered_corpus
+
+    E, off, cl = make_clustered_corpus(4000, (1, 9), 64, seed=5, mean_cluster=200, max_cluster=1500)
+    assert np.allclose(np.linalg.norm(E, axis=1), 1.0, atol=2e-3) and np.array_equal(E, E.astype(np.float16).astype(np.float32))
+    sizes = np.bincount(cl[cl >= 0])
+    tight = np.nonzero((np.arange(len(sizes)) % 4 == 0) & (sizes >= 100))[0]
+    c = tight[np.argmax(sizes[tight])]
+    rows = np.nonzero(cl == c)[0]
+    s = E[rows] @ E[rows[0]]
+    assert (s > 0.998).all()                      # a tight cluster: every member within 2e-3 of every other
+    assert 0.2 < (cl < 0).mean() < 0.3

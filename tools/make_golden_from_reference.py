@@ -9,7 +9,9 @@ installed), but two pieces of the hot path are pure NumPy/SciPy once their impor
 
 * ``raglite/_embed.py``  -- ``embed_strings_with_late_chunking`` / ``_embed_string_batch``
   (token counting, segmenting, largest-remainder split, mean pool, normalise, fp16 cast);
-* ``raglite/_query_adapter.py`` -- ``_optimize_query_target``.
+* ``raglite/_query_adapter.py`` -- ``_optimize_query_target``;
+* ``raglite/_typing.py`` -- the column processors of the ``chunk_embedding.embedding`` column
+  (DuckDB ``FLOAT[d]`` lists, PostgreSQL ``halfvec`` text, ``np.save`` blobs).
 
 This script loads those two files *unmodified from where they lie* under a synthetic ``raglite``
 package whose heavy dependencies are replaced by stubs, and whose embedder is
@@ -134,8 +136,72 @@ def golden_adapter(qa_mod: types.ModuleType) -> None:
     print("adapter_target", sorted(arrays))
 
 
+class _Generic:
+    """Stand-in for SQLAlchemy's generic base classes (``TypeDecorator[...]``, ``UserDefinedType[...]``)."""
+
+    Comparator: type
+
+    def __class_getitem__(cls, item):  # noqa: ANN001, ANN206
+        return cls
+
+    def __init__(self, *a, **k) -> None:  # noqa: ANN002, ANN003
+        pass
+
+
+_Generic.Comparator = _Generic
+
+
+def load_reference_typing() -> types.ModuleType:
+    """``raglite/_typing.py`` unmodified, with SQLAlchemy reduced to the few names its class bodies touch:
+    the column processors (``bind_processor`` / ``result_processor`` / ``process_*``) are pure NumPy."""
+    for name in ("sqlalchemy", "sqlalchemy.engine", "sqlalchemy.ext", "sqlalchemy.ext.compiler", "sqlalchemy.sql",
+                 "sqlalchemy.sql.functions", "sqlalchemy.sql.operators", "sqlalchemy.types"):
+        _stub(name)
+    sys.modules["sqlalchemy.ext.compiler"].compiles = lambda *a, **k: (lambda fn: fn)
+    sys.modules["sqlalchemy.sql.functions"].FunctionElement = _Generic
+    sys.modules["sqlalchemy.engine"].Dialect = object
+    sys.modules["sqlalchemy.sql.operators"].Operators = object
+    t = sys.modules["sqlalchemy.types"]
+    t.Float, t.LargeBinary, t.TypeDecorator, t.TypeEngine, t.UserDefinedType = _Generic, _Generic, _Generic, _Generic, _Generic
+    return _load("raglite._typing_ref", REF / "_typing.py")
+
+
+def golden_table_rows(typing_mod: types.ModuleType) -> None:
+    """What the reference's own column processors write to / read from ``chunk_embedding.embedding``
+    (``_typing.py:57-78, 145-208``) for float16 embeddings as ``_embed.py:140`` produces them."""
+    rng = np.random.default_rng(11)
+    d, n = 24, 40
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    E16 = E.astype(np.float16)
+    # edge values a halfvec / FLOAT[] column can hold: signed zero, subnormals, the largest half, tiny and integral values
+    E16[0, :8] = np.array([0.0, -0.0, 5.96e-8, -5.96e-8, 6.1e-5, 65504.0, -65504.0, 1.0], np.float16)
+    E16[1, :4] = np.array([0.333251953125, 1e-3, 123.0, -0.5], np.float16)
+    duck, pg, npy = typing_mod.DuckDBSingleVec(d), typing_mod.PostgresHalfVec(d), typing_mod.NumpyArray()
+    duck_bind, duck_res = duck.bind_processor(None), duck.result_processor(None, None)
+    pg_bind, pg_res = pg.bind_processor(None), pg.result_processor(None, None)
+    lists = [duck_bind(r) for r in E16]                     # what RAGLite hands DuckDB for FLOAT[d]
+    texts = [pg_bind(r) for r in E16]                       # ... and PostgreSQL for halfvec(d)
+    blobs = [npy.process_bind_param(r, None) for r in E16]  # ... and any other dialect
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        from_text = np.stack([pg_res(t) for t in texts])
+    from_list = np.stack([duck_res(v) for v in lists])
+    from_blob = np.stack([npy.process_result_value(b, None) for b in blobs])
+    counts = rng.integers(1, 5, size=64)
+    row_chunk = np.repeat(np.arange(len(counts)), counts)[:n]
+    np.savez_compressed(
+        GOLDEN / "table_rows.npz", E16=E16, from_text=from_text, from_list=from_list, from_blob=from_blob, row_chunk=row_chunk,
+        texts=np.frombuffer(json.dumps(texts).encode(), dtype=np.uint8),
+        lists=np.frombuffer(json.dumps(lists).encode(), dtype=np.uint8),
+        blobs=np.frombuffer(b"".join(blobs), dtype=np.uint8), blob_len=np.array([len(b) for b in blobs]))
+    print("table_rows", from_text.dtype, from_list.dtype, from_blob.dtype, texts[0][:48])
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
     embed_mod, qa_mod = install_reference_stubs()
     golden_pool(embed_mod)
     golden_adapter(qa_mod)
+    golden_table_rows(load_reference_typing())
