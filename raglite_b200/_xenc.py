@@ -124,7 +124,9 @@ class CrossEncoderEngine:
         w.cls_w, w.cls_b = cls_w.data_ptr(), cls_b.data_ptr()
         self.weights = w
         self._ws: torch.Tensor | None = None
-        self._lock = threading.Lock()   # reference callers rerank from thread pools (_rag.py:317)
+        self._host_bufs: dict[str, torch.Tensor] = {}   # pinned staging (double-buffered inputs / outputs)
+        self._dev_bufs: dict[int, torch.Tensor] = {}
+        self._lock = threading.RLock()   # reference callers rerank from thread pools (_rag.py:317)
 
     # ---- constructors ------------------------------------------------------------------------------
     @classmethod
@@ -150,52 +152,101 @@ class CrossEncoderEngine:
 
     # ---- scoring ---------------------------------------------------------------------------------------
     def score_tokens(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray]) -> tuple[np.ndarray, np.ndarray]:
-        """Logits and sigmoid scores for already-tokenised pairs (variable lengths, no padding)."""
+        """Logits and sigmoid scores for already-tokenised pairs (variable lengths, no padding).
+
+        The pairs are cut into calls of at most ``max_tokens_per_call`` tokens.  Calls are pipelined: while
+        the GPU runs call *i*, the host packs call *i+1* into the other half of a pinned double buffer and
+        enqueues its upload and kernels; results come back through pinned memory and are only waited for
+        once the next call is in the queue -- the host packing disappears behind the forward."""
         P = len(ids)
         logits = np.empty(P, np.float32)
         scores = np.empty(P, np.float32)
-        lens = np.array([len(x) for x in ids], dtype=np.int64)
+        lens = np.fromiter((len(x) for x in ids), dtype=np.int64, count=P)
         if P and lens.max() > self.max_length:
             raise ValueError("sequence longer than max_length")
-        start = 0
-        while start < P:
-            end, tok = start, 0
-            while end < P and (end == start or tok + lens[end] <= self.max_tokens_per_call):
-                tok += int(lens[end])
-                end += 1
-            lo, sc = self._score_packed(ids[start:end], type_ids[start:end], lens[start:end])
-            logits[start:end], scores[start:end] = lo, sc
-            start = end
+        cuts = [0]
+        tok = 0
+        for i in range(P):
+            if i > cuts[-1] and tok + lens[i] > self.max_tokens_per_call:
+                cuts.append(i)
+                tok = 0
+            tok += int(lens[i])
+        cuts.append(P)
+        with self._lock, torch.cuda.device(self.device):
+            pending: tuple[int, int, torch.Tensor, torch.cuda.Event] | None = None
+            for c in range(len(cuts) - 1):
+                lo, hi = cuts[c], cuts[c + 1]
+                if hi == lo:
+                    continue
+                item = self._launch_packed(ids[lo:hi], type_ids[lo:hi], lens[lo:hi], slot=c & 1)
+                if pending is not None:
+                    self._collect(pending, logits, scores)
+                pending = (lo, hi, *item)
+            if pending is not None:
+                self._collect(pending, logits, scores)
         return logits, scores
 
-    def _score_packed(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray], lens: np.ndarray
-                      ) -> tuple[np.ndarray, np.ndarray]:
+    def _collect(self, pending: tuple[int, int, torch.Tensor, torch.cuda.Event], logits: np.ndarray, scores: np.ndarray) -> None:
+        lo, hi, host, ev = pending
+        ev.synchronize()
+        res = host.numpy()[: 2 * (hi - lo)].reshape(2, hi - lo)
+        logits[lo:hi], scores[lo:hi] = res[0], res[1]
+
+    def _pinned(self, name: str, n: int, dtype: torch.dtype) -> torch.Tensor:
+        buf = self._host_bufs.get(name)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1024), dtype=dtype, pin_memory=True)
+            self._host_bufs[name] = buf
+        return buf
+
+    def _launch_packed(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray], lens: np.ndarray, *, slot: int
+                       ) -> tuple[torch.Tensor, torch.cuda.Event]:
+        """Pack one call into pinned buffer ``slot``, enqueue upload + forward + download; returns the pinned
+        result buffer and the event that marks it complete.  Caller holds the lock."""
         P, T = len(ids), int(lens.sum())
-        cu = np.zeros(P + 1, np.int32)
-        cu[1:] = np.cumsum(lens)
-        flat_ids = np.concatenate(ids).astype(np.int32)
-        flat_types = np.concatenate(type_ids).astype(np.int32)
+        n_in = 3 * T + P + 1
+        host_in = self._pinned(f"in{slot}", n_in, torch.int32)
+        h = host_in.numpy()
+        np.concatenate(ids, out=h[:T], casting="unsafe")
+        np.concatenate(type_ids, out=h[T:2 * T], casting="unsafe")
+        cu = h[3 * T:3 * T + P + 1]
+        cu[0] = 0
+        np.cumsum(lens, out=cu[1:])
+        h[2 * T:3 * T] = np.arange(T, dtype=np.int32) - np.repeat(cu[:-1], lens)      # position ids 0..len-1 per pair
         # A tokenizer that does not match the weights would index past the embedding tables.
         w = self.weights
-        if T and (int(flat_ids.min()) < 0 or int(flat_ids.max()) >= w.vocab):
+        if T and (int(h[:T].min()) < 0 or int(h[:T].max()) >= w.vocab):
             raise ValueError(f"token id outside the model's vocabulary [0, {w.vocab}) -- tokenizer / weights mismatch?")
-        if T and (int(flat_types.min()) < 0 or int(flat_types.max()) >= w.type_vocab):
+        if T and (int(h[T:2 * T].min()) < 0 or int(h[T:2 * T].max()) >= w.type_vocab):
             raise ValueError(f"token type id outside [0, {w.type_vocab})")
         if P and int(lens.max()) > w.max_pos:
             raise ValueError(f"sequence longer than the model's {w.max_pos} positions")
-        flat_pos = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
-        host = torch.from_numpy(np.concatenate([flat_ids, flat_types, flat_pos, cu]))
-        dev = host.to(self.device, non_blocking=True)
-        d_ids, d_types, d_pos, d_cu = dev[:T], dev[T:2 * T], dev[2 * T:3 * T], dev[3 * T:]
+        dev = self._dev_bufs.get(slot)
+        if dev is None or dev.numel() < n_in:
+            dev = torch.empty(max(n_in, 1024), dtype=torch.int32, device=self.device)
+            self._dev_bufs[slot] = dev
+        dev[:n_in].copy_(host_in[:n_in], non_blocking=True)
+        d_ids, d_types, d_pos, d_cu = dev[:T], dev[T:2 * T], dev[2 * T:3 * T], dev[3 * T:n_in]
         out = torch.empty((2, P), dtype=torch.float32, device=self.device)
+        need = int(self.lib.rl_xenc_workspace_bytes(C.byref(self.weights), T))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        check(self.lib.rl_xenc_score(C.byref(self.weights), d_ids.data_ptr(), d_types.data_ptr(), d_pos.data_ptr(),
+                                     d_cu.data_ptr(), P, T, int(lens.max()), out[0].data_ptr(), out[1].data_ptr(),
+                                     self._ws.data_ptr(), self._ws.numel(), _stream()), "rl_xenc_score")
+        host_out = self._pinned(f"out{slot}", 2 * P, torch.float32)
+        host_out[: 2 * P].copy_(out.reshape(-1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host_out, ev
+
+    def _score_packed(self, ids: Sequence[np.ndarray], type_ids: Sequence[np.ndarray], lens: np.ndarray
+                      ) -> tuple[np.ndarray, np.ndarray]:
+        """One synchronous call (kept for callers that time a single forward)."""
         with self._lock, torch.cuda.device(self.device):
-            need = int(self.lib.rl_xenc_workspace_bytes(C.byref(self.weights), T))
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            check(self.lib.rl_xenc_score(C.byref(self.weights), d_ids.data_ptr(), d_types.data_ptr(), d_pos.data_ptr(),
-                                         d_cu.data_ptr(), P, T, int(lens.max()), out[0].data_ptr(), out[1].data_ptr(),
-                                         self._ws.data_ptr(), self._ws.numel(), _stream()), "rl_xenc_score")
-            res = out.cpu().numpy()   # (synchronises before the workspace can be reused by another thread)
+            host, ev = self._launch_packed(ids, type_ids, np.asarray(lens, dtype=np.int64), slot=0)
+            ev.synchronize()
+            res = host.numpy()[: 2 * len(ids)].reshape(2, len(ids)).copy()
         return res[0], res[1]
 
     def encode_pairs(self, queries: Sequence[str], docs: Sequence[str]) -> tuple[list[np.ndarray], list[np.ndarray]]:

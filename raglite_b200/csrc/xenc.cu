@@ -611,30 +611,53 @@ __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restr
   }
 }
 
-// ---- pooler + classifier: one warp per sequence -----------------------------------------------------------
+// ---- pooler + classifier ----------------------------------------------------------------------------------
+// logit[s] = Wc . tanh(Wp h_s + bp) + bc with h_s the [CLS] row of sequence s.  A warp owns kClsSeqs
+// sequences (their [CLS] rows sit in shared memory as fp32) and walks the H pooler outputs; for one output
+// the lanes stride over the H inputs, so every Wp read is a coalesced 128-byte line shared by the warp's
+// sequences, followed by one warp-shuffle reduction per sequence.  (The first version read Wp row-per-lane:
+// 32 different lines per load instruction, 313 us per launch -- more than the rest of a small forward.)
+constexpr int kClsSeqs = 4;
 __global__ void __launch_bounds__(128) cls_head_kernel(const __half* __restrict__ hidden, const int32_t* __restrict__ cu,
                                                        const float* __restrict__ Wp, const float* __restrict__ bp,
                                                        const float* __restrict__ Wc, const float* __restrict__ bc, int P, int H,
                                                        float* __restrict__ logit, float* __restrict__ score) {
-  extern __shared__ float cls_smem[];  // [warps][H]
+  extern __shared__ float cls_smem[];  // [warps][kClsSeqs][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int seq = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (seq >= P) return;
-  float* h = cls_smem + (size_t)warp * H;
-  const __half* src = hidden + (size_t)cu[seq] * H;  // [CLS] token
-  for (int c = lane; c < H; c += 32) h[c] = __half2float(src[c]);
-  __syncwarp();
-  float out = 0.f;
-  for (int o = lane; o < H; o += 32) {
-    const float* w = Wp + (size_t)o * H;
-    float a = bp[o];
-    for (int c = 0; c < H; ++c) a = fmaf(w[c], h[c], a);
-    out += tanhf(a) * Wc[o];
+  const int seq0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kClsSeqs;
+  if (seq0 >= P) return;
+  float* h = cls_smem + (size_t)warp * kClsSeqs * H;
+#pragma unroll
+  for (int s = 0; s < kClsSeqs; ++s) {
+    const bool ok = seq0 + s < P;
+    const __half* src = hidden + (size_t)cu[ok ? seq0 + s : seq0] * H;  // [CLS] token
+    for (int c = lane; c < H; c += 32) h[s * H + c] = ok ? __half2float(src[c]) : 0.f;
   }
-  out = warp_sum_f(out) + bc[0];
-  if (lane == 0) {
-    logit[seq] = out;
-    score[seq] = 1.f / (1.f + __expf(-out));  // FlashRank: sigmoid of the single logit
+  __syncwarp();
+  float out[kClsSeqs];
+#pragma unroll
+  for (int s = 0; s < kClsSeqs; ++s) out[s] = 0.f;
+  for (int o = 0; o < H; ++o) {
+    const float* w = Wp + (size_t)o * H;
+    float a[kClsSeqs];
+#pragma unroll
+    for (int s = 0; s < kClsSeqs; ++s) a[s] = 0.f;
+    for (int c = lane; c < H; c += 32) {
+      const float wv = __ldg(w + c);
+#pragma unroll
+      for (int s = 0; s < kClsSeqs; ++s) a[s] = fmaf(wv, h[s * H + c], a[s]);
+    }
+    const float b = __ldg(bp + o), wc = __ldg(Wc + o);
+#pragma unroll
+    for (int s = 0; s < kClsSeqs; ++s) out[s] += tanhf(warp_sum_f(a[s]) + b) * wc;   // identical on every lane
+  }
+  if (lane < kClsSeqs && seq0 + lane < P) {
+    float v = out[0];
+#pragma unroll
+    for (int s = 1; s < kClsSeqs; ++s) v = lane == s ? out[s] : v;
+    v += bc[0];
+    logit[seq0 + lane] = v;
+    score[seq0 + lane] = 1.f / (1.f + __expf(-v));  // FlashRank: sigmoid of the single logit
   }
 }
 
@@ -664,8 +687,11 @@ static int launch_linear(const __half* X, const void* img, const float* bias, __
   t.X = X; t.img = reinterpret_cast<const __half*>(img); t.bias = bias; t.Y = Y; t.T = T; t.N = N; t.K = K; t.act = act;
   t.n_pass = (N + kMaxN - 1) / kMaxN;
   t.n_ks = (K + kSliceK - 1) / kSliceK;
-  const char* cpa = getenv("RL_XENC_CPASYNC");   // read per launch: tools/time_linear.py A/Bs it in one process
-  t.cp_async = (cpa != nullptr && atoi(cpa) != 0) ? 1 : 0;
+  // cp.async activation loader (every free smem stage in flight, no registers held) is the default: bit-identical
+  // outputs, 352 -> 309 us for the four GEMMs of a layer (profiles/r01_linear_loader_ab.json); RL_XENC_CPASYNC=0
+  // selects the register-ring loader.  Read per launch: tools/time_linear.py A/Bs it in one process.
+  const char* cpa = getenv("RL_XENC_CPASYNC");
+  t.cp_async = (cpa != nullptr && atoi(cpa) == 0) ? 0 : 1;
   static_assert((2 * kMaxStages + 4) * 8 + 8 <= kBarBytes, "barrier block overflows its slot");
   const uint32_t tail = kBarBytes + kEpiBytes;
   int stages = (int)((kSmemBudget - 1024 - tail) / lin_stage_bytes());
@@ -753,8 +779,8 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     add_ln_kernel<<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln2_g, L.ln2_b, w->ln_eps, T, H, hidden);
     RL_CUDA_CHECK(cudaGetLastError());
   }
-  cls_head_kernel<<<(P + 3) / 4, 128, (size_t)4 * H * sizeof(float), stream>>>(hidden, cu_seqlens, w->pooler_w, w->pooler_b,
-                                                                                w->cls_w, w->cls_b, P, H, out_logit, out_score);
+  cls_head_kernel<<<(P + 4 * kClsSeqs - 1) / (4 * kClsSeqs), 128, (size_t)4 * kClsSeqs * H * sizeof(float), stream>>>(
+      hidden, cu_seqlens, w->pooler_w, w->pooler_b, w->cls_w, w->cls_b, P, H, out_logit, out_score);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }
