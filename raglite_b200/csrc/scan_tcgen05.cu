@@ -56,7 +56,9 @@ struct TcArgs {
   const __half* qimg;     // [n_ks][nq][64] fp16, rows pre-swizzled
   const float* q_scale;   // [B] key = acc * q_scale[b] (+ bias)
   const float* row_stats; // [2] max norm, max |element|
-  int nq;                 // padded #queries of this pass (multiple of 16)
+  int nq;                 // padded #queries of a FULL group (multiple of 16; kMaxQ when n_groups > 1)
+  int n_groups;           // query groups of kMaxQ walked per corpus tile (B <= n_groups * kMaxQ)
+  int nq_last;            // padded #queries of the last group
   int n_ks;               // K slices
   int stages;
   int tmem_cols;          // allocated TMEM columns (power of two >= 2 * buf_cols)
@@ -87,8 +89,14 @@ struct SmemLayout {
 };
 
 __host__ __device__ inline uint32_t stage_bytes(int nq) { return kABytes + (uint32_t)nq * 128u; }
-__host__ __device__ inline uint32_t tail_bytes() {
-  return (2 * kMaxStages + 4) * 8 + 16 + 6 * kMaxQ * 4 + kMaxQ * kHistBins * 2 + 16 + kListCap * 12;
+// One query group (B <= 256): thresholds, scales, histogram origin / bin width, the staged histogram and the
+// per-query counters all live in shared memory.  Several groups per tile (B > 256, configs[2]): only
+// thresholds, scales and counters (the histogram is updated with global atomics at hit time, its origin
+// and bin width are read from global memory there) -- that keeps four pipeline stages.
+__host__ __device__ inline uint32_t tail_bytes(int n_groups) {
+  const uint32_t qt = (uint32_t)n_groups * kMaxQ;
+  const uint32_t per_q = n_groups > 1 ? 4u * 4u : 6u * 4u + (uint32_t)kHistBins * 2u;
+  return (2 * kMaxStages + 4) * 8 + 16 + qt * per_q + 16 + kListCap * 12;
 }
 
 // PAIR: two CTAs of a cluster (an SM pair) issue one cta_group::2 MMA (M = 256: 128 rows per CTA) and
@@ -102,7 +110,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   // 1024-byte alignment for the 128B-swizzled tiles.
   // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const uint32_t sbytes = stage_bytes(PAIR ? t.nq / 2 : t.nq);
+  const uint32_t sbytes = stage_bytes(PAIR ? t.nq / 2 : t.nq);   // sized by a full group
   SmemLayout s;
   s.stage_base = base;
   s.full = reinterpret_cast<uint64_t*>(base + (size_t)t.stages * sbytes);
@@ -110,14 +118,22 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   s.tmem_full = s.empty + kMaxStages;
   s.tmem_empty = s.tmem_full + 2;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
+  const int G = t.n_groups;
+  const bool multi = G > 1;
+  const int QT = G * kMaxQ;            // query slots of this launch
   s.thr = reinterpret_cast<float*>(s.tmem_ptr + 4);
-  s.cs = s.thr + kMaxQ;
-  s.thr0 = s.cs + kMaxQ;
-  s.inv_w = s.thr0 + kMaxQ;
-  s.hist = reinterpret_cast<uint32_t*>(s.inv_w + kMaxQ);
-  s.cnt = reinterpret_cast<int*>(s.hist + kMaxQ * kHistBins / 2);
-  s.basev = s.cnt + kMaxQ;
-  s.list_n = s.basev + kMaxQ;
+  s.cs = s.thr + QT;
+  if (!multi) {
+    s.thr0 = s.cs + QT;
+    s.inv_w = s.thr0 + QT;
+    s.hist = reinterpret_cast<uint32_t*>(s.inv_w + QT);
+    s.cnt = reinterpret_cast<int*>(s.hist + QT * kHistBins / 2);
+  } else {
+    s.thr0 = nullptr; s.inv_w = nullptr; s.hist = nullptr;
+    s.cnt = reinterpret_cast<int*>(s.cs + QT);
+  }
+  s.basev = s.cnt + QT;
+  s.list_n = s.basev + QT;
   s.list = reinterpret_cast<uint32_t*>(s.list_n + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +148,10 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     const int64_t unit = first + tile * stride;
     return PAIR ? 2 * unit + rank : unit;
   };
+  // B > 256: every corpus tile is walked once per query group, back to back (group-minor order), so the
+  // re-reads of the tile hit L2 and HBM sees the corpus once.  "Virtual tile" v = tile * n_groups + group.
+  const int G0 = t.n_groups;
+  const int64_t v_tiles = my_tiles * G0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < t.stages; ++i) {
@@ -145,14 +165,17 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < kMaxQ; i += blockDim.x) {
+  for (int i = threadIdx.x; i < QT; i += blockDim.x) {
     s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
     s.cs[i] = (i < a.B) ? t.q_scale[i] : 0.f;
     s.cnt[i] = 0;
-    s.thr0[i] = s.thr[i];
-    s.inv_w[i] = (i < a.B && !a.dump_mode) ? a.hist_inv_w[i] : 0.f;
+    if (!multi) {
+      s.thr0[i] = s.thr[i];
+      s.inv_w[i] = (i < a.B && !a.dump_mode) ? a.hist_inv_w[i] : 0.f;
+    }
   }
-  for (int i = threadIdx.x; i < kMaxQ * kHistBins / 2; i += blockDim.x) s.hist[i] = 0u;
+  if (!multi)
+    for (int i = threadIdx.x; i < kMaxQ * kHistBins / 2; i += blockDim.x) s.hist[i] = 0u;
   if (threadIdx.x == 0) { s.list_n[0] = 0; s.list_n[1] = 0; }
   if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_2cta(s.tmem_ptr, (uint32_t)t.tmem_cols);
@@ -179,16 +202,16 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
     const __half2 gs2 = __float2half2_rn(gscale);   // exact power of two (dot / l2 only)
     const bool scale = gscale != 1.f;
-    const int64_t total_items = my_tiles * t.n_ks;
+    const int64_t total_items = v_tiles * t.n_ks;
     const size_t pitch32_bytes = (size_t)a.ld * 32 * sizeof(__half);
     const size_t slice_bytes = kSliceK * sizeof(__half);
     uint4 ring[4][4];
     int64_t ld_tile = 0;
     int ld_ks = 0, ld_rows = 0;
     const unsigned char* ld_ptr = nullptr;
-    auto ld_set_tile = [&]() {
-      if (ld_tile < my_tiles && ord_of(ld_tile) < a.n_mode_blocks) {
-        const int64_t blk = mode_block_index(a, ord_of(ld_tile));
+    auto ld_set_tile = [&]() {   // ld_tile / pf_tile count virtual tiles
+      if (ld_tile < v_tiles && ord_of(ld_tile / G0) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(ld_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         ld_rows = rem < kTileM ? (int)rem : kTileM;
         ld_ptr = reinterpret_cast<const unsigned char*>(Eh + (size_t)(blk * kTileM + r0) * a.ld + j * 8);
@@ -199,9 +222,9 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int64_t pf_tile = 0;
     int pf_ks = 0, pf_rows = 0;
     const unsigned char* pf_ptr = nullptr;
-    auto pf_set_tile = [&]() {
-      if (pf_tile < my_tiles && ord_of(pf_tile) < a.n_mode_blocks) {
-        const int64_t blk = mode_block_index(a, ord_of(pf_tile));
+    auto pf_set_tile = [&]() {   // only the first group's pass over a tile comes from HBM
+      if (pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(pf_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         pf_rows = rem < kTileM ? (int)rem : kTileM;
         pf_ptr = reinterpret_cast<const unsigned char*>(Eh + (size_t)(blk * kTileM + (lt & 127)) * a.ld);
@@ -277,7 +300,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     // Rows are converted without a multiply when no scaling is needed (normalised corpora: the
     // cosine 1/|e| then moves to the epilogue, which has slack; dot/l2: the global scale is 1).
     const bool noscale = (METRIC == RL_METRIC_COSINE) ? cos_noscale : (gscale == 1.f);
-    const int64_t total_items = my_tiles * t.n_ks;
+    const int64_t total_items = v_tiles * t.n_ks;
     float4 ring[2][8];
     float rs[8];
 
@@ -288,9 +311,9 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int64_t ld_tile = 0;
     int ld_ks = 0, ld_rows = 0;
     const unsigned char* ld_ptr = nullptr;                 // row r0 of the tile, column c4*4 + ld_ks*64
-    auto ld_set_tile = [&]() {
-      if (ld_tile < my_tiles && ord_of(ld_tile) < a.n_mode_blocks) {
-        const int64_t blk = mode_block_index(a, ord_of(ld_tile));
+    auto ld_set_tile = [&]() {   // ld_tile / pf_tile / st_tile count virtual tiles
+      if (ld_tile < v_tiles && ord_of(ld_tile / G0) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(ld_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         ld_rows = rem < kTileM ? (int)rem : kTileM;
         ld_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + r0) * a.ld + c4 * 4);
@@ -302,9 +325,9 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int64_t pf_tile = 0;
     int pf_ks = 0, pf_rows = 0;
     const unsigned char* pf_ptr = nullptr;
-    auto pf_set_tile = [&]() {
-      if (pf_tile < my_tiles && ord_of(pf_tile) < a.n_mode_blocks) {
-        const int64_t blk = mode_block_index(a, ord_of(pf_tile));
+    auto pf_set_tile = [&]() {   // only the first group's pass over a tile comes from HBM
+      if (pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(pf_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         pf_rows = rem < kTileM ? (int)rem : kTileM;
         pf_ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + (lt >> 1)) * a.ld + (lt & 1) * 32);
@@ -356,8 +379,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     auto fetch_scales = [&](int64_t tile) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) rs[i] = (METRIC == RL_METRIC_COSINE) ? 0.f : gscale;
-      if (METRIC == RL_METRIC_COSINE && !noscale && tile < my_tiles && ord_of(tile) < a.n_mode_blocks) {
-        const int64_t blk = mode_block_index(a, ord_of(tile));
+      if (METRIC == RL_METRIC_COSINE && !noscale && tile < v_tiles && ord_of(tile / G0) < a.n_mode_blocks) {
+        const int64_t blk = mode_block_index(a, ord_of(tile / G0));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int64_t row = blk * kTileM + r0 + 16 * i;
@@ -416,18 +439,22 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   } else if (warp == kQWarp) {
     // ===== query producer: bulk-copy the pre-swizzled fp16 K slice of all queries (UMMA B operand) =====
     if (lane == 0) {
-      const uint32_t slice_bytes_q = (uint32_t)t.nq * 128u;                 // one K slice of all queries
-      const uint32_t qbytes = PAIR ? slice_bytes_q / 2 : slice_bytes_q;     // PAIR: this CTA's half of the queries
-      const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(t.qimg) + (PAIR ? (size_t)rank * qbytes : 0);
-      const int64_t total_items = my_tiles * t.n_ks;
-      int ks = 0, stage = 0;
+      // Group g's image starts g * (n_ks * kMaxQ * kSliceK) halves into qimg; inside a group the K slices of
+      // its nq_g queries follow each other (nq_g * 128 bytes each).
+      const size_t group_bytes = (size_t)t.n_ks * kMaxQ * kSliceK * sizeof(__half);
+      const int64_t total_items = v_tiles * t.n_ks;
+      int ks = 0, stage = 0, g = 0;
       uint32_t phase = 0;
       for (int64_t item = 0; item < total_items; ++item) {
+        const uint32_t slice_bytes_q = (uint32_t)(g == G0 - 1 ? t.nq_last : t.nq) * 128u;   // one K slice of the group's queries
+        const uint32_t qbytes = PAIR ? slice_bytes_q / 2 : slice_bytes_q;                    // PAIR: this CTA's half of them
+        const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(t.qimg) + (size_t)g * group_bytes +
+                                    (PAIR ? (size_t)rank * qbytes : 0);
         mbar_wait(&s.empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&s.full[stage], qbytes);
         bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes, qsrc + (size_t)ks * slice_bytes_q, qbytes,
                  &s.full[stage]);
-        if (++ks == t.n_ks) ks = 0;
+        if (++ks == t.n_ks) { ks = 0; if (++g == G0) g = 0; }
         if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -439,7 +466,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const int64_t total_items = my_tiles * t.n_ks;
+        const int64_t total_items = v_tiles * t.n_ks;
         for (int64_t item = 0; item < total_items; ++item) {
           mbar_wait(&s.full[stage], phase);
           fence_proxy_async();
@@ -448,10 +475,13 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
         }
       }
     } else if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq);
-      int stage = 0;
+      const uint32_t idesc_full = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq);
+      const uint32_t idesc_last = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq_last);
+      int stage = 0, g = 0;
       uint32_t phase = 0;
-      for (int64_t tile = 0; tile < my_tiles; ++tile) {
+      for (int64_t tile = 0; tile < v_tiles; ++tile) {   // virtual tiles: (corpus tile, query group)
+        const uint32_t idesc = g == G0 - 1 ? idesc_last : idesc_full;
+        if (++g == G0) g = 0;
         const int buf = (int)(tile & 1);
         if (PAIR) mbar_wait_cluster(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
         else mbar_wait(&s.tmem_empty[buf], (uint32_t)(((tile >> 1) & 1) ^ 1));
@@ -485,8 +515,12 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     // ===== epilogue warps 0..3: TMEM -> registers -> key -> dump / threshold + emit =====
     const int q = warp;  // TMEM lane quarter
     bool flushed_once = false;
-    for (int64_t tile = 0; tile < my_tiles; ++tile) {
-      const int buf = (int)(tile & 1);
+    int g = 0;           // query group of the current virtual tile
+    for (int64_t vt = 0; vt < v_tiles; ++vt) {
+      const int64_t tile = multi ? vt / G0 : vt;   // corpus tile
+      const int q0 = g * kMaxQ;                    // first query slot of this group
+      const int nq_g = g == G0 - 1 ? t.nq_last : t.nq;
+      const int buf = (int)(vt & 1);
       const int64_t ord = ord_of(tile);
       const bool has_block = ord < a.n_mode_blocks;
       const int64_t blk = has_block ? mode_block_index(a, ord) : 0;
@@ -496,7 +530,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       if (valid && a.row_allowed != nullptr) valid = a.row_allowed[row] != 0;
       const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
       const float lane_scale = (METRIC == RL_METRIC_COSINE && cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
-      mbar_wait(&s.tmem_full[buf], (uint32_t)((tile >> 1) & 1));
+      mbar_wait(&s.tmem_full[buf], (uint32_t)((vt >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * t.buf_cols);
       // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is processed.
@@ -504,7 +538,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
         if (a.dump_mode) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
+            const int col = q0 + c0 + j;
             if (col < a.B) {
               float key = __uint_as_float(v[j]);
               if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
@@ -517,30 +551,33 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float key = __uint_as_float(v[j]);
-            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[q0 + c0 + j], bias);
             else key *= lane_scale;
-            if (key >= s.thr[c0 + j]) mask |= 1u << j;
+            if (key >= s.thr[q0 + c0 + j]) mask |= 1u << j;
           }
           if (!valid) mask = 0;
           while (mask != 0) {  // rare: a few hits per tile; picks v[j] with a register select tree
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
+            const int col = q0 + c0 + j;
             float key = __uint_as_float(select32(v, j));
-            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + j], bias);
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
             else key *= lane_scale;
             // Stage the hit in shared memory (one returning atomic for the slot; the histogram update
             // does not wait); per-query ranks and global slots are handed out in bulk at the flush.
             const int pos = atomicAdd(&s.list_n[0], 1);
-            {
-              const int hb = (c0 + j) * kHistBins + hist_bin(key, s.thr0[c0 + j], s.inv_w[c0 + j]);
+            if (!multi) {
+              const int hb = col * kHistBins + hist_bin(key, s.thr0[col], s.inv_w[col]);
               atomicAdd(&s.hist[hb >> 1], 1u << ((hb & 1) * 16));
+            } else {   // several groups per tile: the histogram lives in global memory only (fire-and-forget RED)
+              atomicAdd(a.ghist + (size_t)col * kHistBins + hist_bin(key, __ldg(a.thr + col), __ldg(a.hist_inv_w + col)), 1);
             }
             if (pos < kListCap) {
-              s.list[pos * 3 + 0] = (uint32_t)(c0 + j);
+              s.list[pos * 3 + 0] = (uint32_t)col;
               s.list[pos * 3 + 1] = __float_as_uint(key);
               s.list[pos * 3 + 2] = (uint32_t)row;
             } else {
-              emit_candidate(a, c0 + j, key, (int32_t)row);
+              emit_candidate(a, col, key, (int32_t)row);
             }
           }
         }
@@ -548,20 +585,20 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       uint32_t va[32], vb[32];
       tmem_ld32_async(taddr0, va);
       tmem_ld_wait(va);
-      for (int c0 = 0; c0 < t.nq; c0 += 64) {
-        const bool has_b = c0 + 32 < t.nq;
+      for (int c0 = 0; c0 < nq_g; c0 += 64) {
+        const bool has_b = c0 + 32 < nq_g;
         if (has_b) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 32), vb);
         process_chunk(c0, va);
         if (has_b) {
           tmem_ld_wait(vb);
-          if (c0 + 64 < t.nq) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 64), va);
+          if (c0 + 64 < nq_g) tmem_ld32_async(taddr0 + (uint32_t)(c0 + 64), va);
           process_chunk(c0 + 32, vb);
-          if (c0 + 64 < t.nq) tmem_ld_wait(va);
+          if (c0 + 64 < nq_g) tmem_ld_wait(va);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {  // TMEM buffer is free for tile + 2 (the leader CTA's barrier counts both epilogues)
+      if (lane == 0) {  // TMEM buffer is free for virtual tile + 2 (the leader CTA's barrier counts both epilogues)
         if (PAIR && rank != 0) mbar_arrive_remote(mapa_u32(&s.tmem_empty[buf], 0));
         else mbar_arrive(&s.tmem_empty[buf]);
       }
@@ -573,7 +610,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
         epi_bar_sync();
         const int n_all = s.list_n[0];
         epi_bar_sync();
-        const bool last = tile + 1 == my_tiles;
+        const bool last = vt + 1 == v_tiles;
         const bool do_flush = n_all >= (flushed_once ? kFlushAt : kFlushFirst) || (last && n_all > 0);
         if (do_flush) {
           flushed_once = true;
@@ -583,19 +620,21 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             s.list[e * 3 + 0] = (uint32_t)col | ((uint32_t)atomicAdd(&s.cnt[col], 1) << 16);
           }
           epi_bar_sync();
-          for (int col = et; col < kMaxQ; col += kNumEpiWarps * 32) {
+          for (int col = et; col < QT; col += kNumEpiWarps * 32) {
             const int c = s.cnt[col];
             if (c > 0) {
               s.basev[col] = atomicAdd(a.cand_cnt + col, c);
               s.cnt[col] = 0;
             }
           }
-          for (int w = et; w < kMaxQ * kHistBins / 2; w += kNumEpiWarps * 32) {
-            const uint32_t h = s.hist[w];
-            if (h != 0u) {
-              if (h & 0xFFFFu) atomicAdd(a.ghist + 2 * w, (int)(h & 0xFFFFu));
-              if (h >> 16) atomicAdd(a.ghist + 2 * w + 1, (int)(h >> 16));
-              s.hist[w] = 0u;
+          if (!multi) {
+            for (int w = et; w < kMaxQ * kHistBins / 2; w += kNumEpiWarps * 32) {
+              const uint32_t h = s.hist[w];
+              if (h != 0u) {
+                if (h & 0xFFFFu) atomicAdd(a.ghist + 2 * w, (int)(h & 0xFFFFu));
+                if (h >> 16) atomicAdd(a.ghist + 2 * w + 1, (int)(h >> 16));
+                s.hist[w] = 0u;
+              }
             }
           }
           epi_bar_sync();
@@ -608,10 +647,13 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
               a.cand[(size_t)col * a.cap + slot] = Cand{__uint_as_float(s.list[e * 3 + 1]), (int32_t)s.list[e * 3 + 2]};
           }
         }
-        if ((do_flush || (tile % kRefreshEvery) == kRefreshEvery - 1) && !last) {
+        const bool periodic = (tile % kRefreshEvery) == kRefreshEvery - 1;
+        if ((do_flush || periodic) && !last) {
           // Threshold refresh: the highest bin edge with >= sel_count candidates at or above it (all
           // CTAs' hits so far) bounds the sel_count-th best key from below; emit from 2 eps under it.
-          for (int col = et; col < a.B; col += kNumEpiWarps * 32) {
+          // (Several groups per tile: the group just processed is refreshed -- each group every 16 tiles.)
+          const int c_lo = multi ? q0 : 0, c_hi = multi ? min(a.B, q0 + kMaxQ) : a.B;
+          for (int col = c_lo + et; col < c_hi; col += kNumEpiWarps * 32) {
             const int4* gh = reinterpret_cast<const int4*>(a.ghist + (size_t)col * kHistBins);
             int cnts[kHistBins];
 #pragma unroll
@@ -627,15 +669,17 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             }
             if (best >= 1) {
               // edge = thr0 + best * w; new emission threshold = edge - 2 eps
-              if (s.inv_w[col] > 0.f) {
-                const float nt = s.thr0[col] + (float)best / s.inv_w[col] - 2.f * a.eps[col];
+              const float iw = multi ? __ldg(a.hist_inv_w + col) : s.inv_w[col];
+              if (iw > 0.f) {
+                const float nt = (multi ? __ldg(a.thr + col) : s.thr0[col]) + (float)best / iw - 2.f * a.eps[col];
                 if (nt > s.thr[col]) s.thr[col] = nt;
               }
             }
           }
         }
-        if (do_flush || (tile % kRefreshEvery) == kRefreshEvery - 1) epi_bar_sync();
+        if (do_flush || periodic) epi_bar_sync();
       }
+      if (++g == G0) g = 0;
     }
   }
 
@@ -712,16 +756,27 @@ int tcgen05_prepare_queries(const rl_scan_params* p, const float* q_inv_norm, fl
   return RL_OK;
 }
 
+constexpr int kMaxGroups = 4;   // query groups walked per corpus tile in one launch (B <= 1024 per launch)
+
 int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const float* q_scale, const void* qimg,
                         int sm_count, cudaStream_t stream) {
   if (a_in.n_mode_blocks == 0 || a_in.B == 0) return RL_OK;
   const int n_ks = (p->d + kSliceK - 1) / kSliceK;
   const int groups = (a_in.B + kMaxQ - 1) / kMaxQ;
-  for (int g = 0; g < groups; ++g) {
+  // Up to kMaxGroups groups of 256 queries share one launch: the kernel walks every corpus tile once per
+  // group, back to back, so HBM sees the corpus once per launch (configs[2], B = 1024: one pass instead of
+  // four).  RL_TC_GROUPS=1 restores one launch per group (A/B switch).
+  static const int max_groups = []() {
+    const char* e = getenv("RL_TC_GROUPS");
+    const int v = e ? atoi(e) : kMaxGroups;
+    return v < 1 ? 1 : (v > kMaxGroups ? kMaxGroups : v);
+  }();
+  for (int g0 = 0; g0 < groups; g0 += max_groups) {
     TcArgs t;
     t.a = a_in;
-    const int q0 = g * kMaxQ;
-    const int nb = a_in.B - q0 < kMaxQ ? a_in.B - q0 : kMaxQ;
+    const int q0 = g0 * kMaxQ;
+    const int ng = groups - g0 < max_groups ? groups - g0 : max_groups;
+    const int nb = a_in.B - q0 < ng * kMaxQ ? a_in.B - q0 : ng * kMaxQ;
     t.a.B = nb;
     t.a.thr = a_in.thr + q0;
     t.a.dump = a_in.dump + (size_t)q0 * a_in.n_sample_rows;
@@ -731,10 +786,13 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.a.eps = a_in.eps + q0;
     t.a.hist_inv_w = a_in.hist_inv_w + q0;
     t.a.q_inv_norm = a_in.q_inv_norm + q0;
-    t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g * n_ks * kMaxQ * kSliceK;
+    t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g0 * n_ks * kMaxQ * kSliceK;
     t.q_scale = q_scale + q0;
     t.row_stats = p->row_stats;
-    t.nq = (nb + 15) / 16 * 16;
+    t.n_groups = ng;
+    const int last_b = nb - (ng - 1) * kMaxQ;              // queries of the last group
+    t.nq_last = (last_b + 15) / 16 * 16;
+    t.nq = ng > 1 ? kMaxQ : t.nq_last;                     // a full group (the only group when ng == 1)
     t.n_ks = n_ks;
     t.buf_cols = (t.nq + 31) / 32 * 32;
     int cols = 32;
@@ -744,13 +802,14 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     // B200 (15.1 ms vs 12.6 ms on the 61 GB shard, same box: the peer->leader barrier relay and the
     // coupling of two SMs cost more than the halved query stream saves), so it is opt-in: RL_TC_PAIR=1.
     static const int pair_env = []() { const char* e = getenv("RL_TC_PAIR"); return e ? atoi(e) : 0; }();
-    const bool pair = pair_env == 1 && t.nq % 32 == 0 && t.nq >= 64 && a_in.n_mode_blocks >= 2 && sm_count >= 2;
-    const uint32_t avail = kSmemBudget - 1024 - tail_bytes();
+    const bool pair = pair_env == 1 && t.nq % 32 == 0 && t.nq_last % 32 == 0 && t.nq_last >= 64 && a_in.n_mode_blocks >= 2 &&
+                      sm_count >= 2;
+    const uint32_t avail = kSmemBudget - 1024 - tail_bytes(ng);
     int stages = (int)(avail / stage_bytes(pair ? t.nq / 2 : t.nq));
     if (stages > kMaxStages) stages = kMaxStages;
     RL_REQUIRE(stages >= 2, RL_EUNSUPPORTED, "tcgen05 scan: not enough shared memory for 2 stages");
     t.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes(pair ? t.nq / 2 : t.nq) + tail_bytes() + 1024;
+    const size_t smem = (size_t)stages * stage_bytes(pair ? t.nq / 2 : t.nq) + tail_bytes(ng) + 1024;
     RL_REQUIRE(p->row_stats != nullptr, RL_EINVAL, "tcgen05 scan needs row_stats");
     auto launch = [&](auto kernel, bool is_pair) -> int {
       RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
