@@ -10,7 +10,10 @@
 //   attention_kernel     softmax(Q K^T / sqrt(dh)) V per (sequence, head), fp32 math
 //   add_ln_kernel        LayerNorm(x + residual)
 //   cls_head_kernel      pooler (dense + tanh on [CLS]) -> classifier -> logit, sigmoid score
+#include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "tcgen05_ptx.cuh"
@@ -69,27 +72,36 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // ---- weight image: W[N, K] fp32 row-major -> per (pass, k-slice) swizzled fp16 UMMA B tiles -------------
-__host__ __device__ inline int pass_rows(int N, int pass) {
-  const int rem = N - pass * kMaxN;
-  return rem < kMaxN ? rem : kMaxN;
+// Output columns per pass.  Short-K layers whose width is a multiple of 192 (QKV, out-proj, FFN-up of the
+// MiniLM shapes: K = 384, N = 1152 / 384 / 1536) use 192-column passes: the whole K extent of such a pass
+// (192 x 384 fp16 = 144 KB) stays RESIDENT in shared memory while the CTA walks the token tiles
+// (linear_wres_kernel).  Everything else streams 256-column weight slices (linear_tcgen05_kernel).
+constexpr int kResN = 192;
+constexpr int kResMaxKs = 6;
+__host__ __device__ inline bool use_resident(int N, int K) { return K % kSliceK == 0 && K / kSliceK <= kResMaxKs && N % kResN == 0; }
+__host__ __device__ inline int pass_width(int N, int K) { return use_resident(N, K) ? kResN : kMaxN; }
+
+__host__ __device__ inline int pass_rows(int N, int pass, int pw = kMaxN) {
+  const int rem = N - pass * pw;
+  return rem < pw ? rem : pw;
 }
-__host__ __device__ inline size_t pass_offset_halves(int N, int K, int pass) {
+__host__ __device__ inline size_t pass_offset_halves(int N, int K, int pass, int pw = kMaxN) {
   const int n_ks = (K + kSliceK - 1) / kSliceK;
-  return (size_t)pass * kMaxN * n_ks * kSliceK;  // full passes precede; only the last pass is short
+  return (size_t)pass * pw * n_ks * kSliceK;  // full passes precede; only the last pass is short
 }
 
-__global__ void pack_linear_kernel(const float* __restrict__ W, int N, int K, __half* __restrict__ img) {
+__global__ void pack_linear_kernel(const float* __restrict__ W, int N, int K, int pw, __half* __restrict__ img) {
   const int n_ks = (K + kSliceK - 1) / kSliceK;
   const int64_t total = (int64_t)((N + 15) / 16 * 16) * n_ks * kSliceK;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(idx / (n_ks * kSliceK));
     const int kk = (int)(idx % (n_ks * kSliceK));
-    const int pass = n / kMaxN, r = n % kMaxN;
-    const int nb = (pass_rows(N, pass) + 15) / 16 * 16;
+    const int pass = n / pw, r = n % pw;
+    const int nb = (pass_rows(N, pass, pw) + 15) / 16 * 16;
     const int ks = kk / kSliceK, e = kk % kSliceK;
     const float v = (n < N && kk < K) ? W[(size_t)n * K + kk] : 0.f;
-    const size_t off = pass_offset_halves(N, K, pass) + ((size_t)ks * nb + r) * kSliceK +
+    const size_t off = pass_offset_halves(N, K, pass, pw) + ((size_t)ks * nb + r) * kSliceK +
                        (size_t)((((e >> 3) ^ (r & 7)) << 3) + (e & 7));
     img[off] = __float2half_rn(v);
   }
@@ -104,6 +116,7 @@ struct LinArgs {
   int T, N, K, act;    // act: 0 none, 1 GELU(erf)
   int n_pass, n_ks, stages;
   int cp_async;        // 1: activation tile through cp.async (no register staging; every free stage in flight)
+  int pw;              // output columns per pass of the weight image (pass_width(N, K))
 };
 
 // 16-byte asynchronous global -> shared copy (zero-fills when src_bytes == 0) and the mbarrier arrive
@@ -229,9 +242,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       for (int64_t it = 0; it < my_items; ++it) {
         const int64_t item = first + it * stride;
         const int pass = (int)(item % t.n_pass);
-        const int nb = (pass_rows(t.N, pass) + 15) / 16 * 16;
+        const int nb = (pass_rows(t.N, pass, t.pw) + 15) / 16 * 16;
         const uint32_t wbytes = (uint32_t)nb * 128u;
-        const __half* src = t.img + pass_offset_halves(t.N, t.K, pass);
+        const __half* src = t.img + pass_offset_halves(t.N, t.K, pass, t.pw);
         for (int ks = 0; ks < t.n_ks; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], wbytes);
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       for (int64_t it = 0; it < my_items; ++it) {
         const int64_t item = first + it * stride;
         const int pass = (int)(item % t.n_pass);
-        const int nb = (pass_rows(t.N, pass) + 15) / 16 * 16;
+        const int nb = (pass_rows(t.N, pass, t.pw) + 15) / 16 * 16;
         const uint32_t idesc = make_idesc_f16(kTileM, nb);
         const int buf = (int)(it & 1);
         mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -280,8 +293,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
     for (int64_t it = 0; it < my_items; ++it) {
       const int64_t item = first + it * stride;
       const int m_tile = (int)(item / t.n_pass), pass = (int)(item % t.n_pass);
-      const int nb = pass_rows(t.N, pass);
-      const int n0 = pass * kMaxN;
+      const int nb = pass_rows(t.N, pass, t.pw);
+      const int n0 = pass * t.pw;
       const int buf = (int)(it & 1);
       const int row_base = m_tile * kTileM + q * 32;
       mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
@@ -327,6 +340,171 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- tcgen05 linear layer, weights resident in shared memory, activations through a TMA tensor map ---------
+// For K <= 384 and N % 192 == 0.  A CTA owns ONE 192-column pass of the output for the whole launch: it
+// bulk-copies that pass of the pre-swizzled weight image (n_ks x 24 KB) into shared memory once and then
+// walks token tiles.  Per 128-token tile only the activations move: one thread issues a 2-D
+// cp.async.bulk.tensor (TMA tensor map over X[T, K], box 64 x 128, SWIZZLE_128B -- the layout the UMMA
+// A descriptor expects; rows past T are zero-filled by the hardware) per K slice.  That takes the L2 -> SM
+// traffic per tile from 288 KB (activations + a 256-column weight slice per tile) to 96 KB and frees the
+// eight loader warps: twelve epilogue warps (three per TMEM lane quarter, two 32-column chunks each) now
+// drain a 128 x 192 accumulator while the next tile's MMAs run into the other TMEM buffer.
+constexpr int kResEpiWarps = 12;
+constexpr int kResProdWarp = 12;
+constexpr int kResMmaWarp = 13;
+constexpr int kResThreads = 14 * 32;
+constexpr int kResStages = 3;
+constexpr uint32_t kResWSliceBytes = kResN * 128u;                    // one K slice of the pass: 24 KB
+constexpr uint32_t kResEpiBytes = kResEpiWarps * kEpiWarpBytes;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kResThreads, 1) linear_wres_kernel(const __grid_constant__ CUtensorMap tmA, const LinArgs t) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* w_smem = base;                                               // [n_ks][192 x 128 B]
+  unsigned char* a_smem = w_smem + (size_t)t.n_ks * kResWSliceBytes;          // [kResStages][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + (size_t)kResStages * kABytes);
+  uint64_t* a_full = bars;                   // [kResStages]
+  uint64_t* a_empty = a_full + kResStages;   // [kResStages]
+  uint64_t* tmem_full = a_empty + kResStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* w_full = tmem_empty + 2;            // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
+  unsigned char* epi_stage = reinterpret_cast<unsigned char*>(bars) + kBarBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (t.T + kTileM - 1) / kTileM;
+  // grid = n_pass * ctas_per_pass: CTA c serves pass c % n_pass and token tiles c / n_pass, + ctas_per_pass, ...
+  const int pass = (int)(blockIdx.x % (unsigned)t.n_pass);
+  const int first = (int)(blockIdx.x / (unsigned)t.n_pass), stride = (int)(gridDim.x / (unsigned)t.n_pass);
+  const int my_items = first < m_tiles ? (m_tiles - first + stride - 1) / stride : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kResStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kResEpiWarps);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kResMmaWarp) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == kResProdWarp) {
+    if (lane == 0 && my_items > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      // the pass's weights: resident for the whole launch
+      const __half* wsrc = t.img + pass_offset_halves(t.N, t.K, pass, kResN);
+      mbar_arrive_expect_tx(w_full, (uint32_t)t.n_ks * kResWSliceBytes);
+      for (int ks = 0; ks < t.n_ks; ++ks)
+        bulk_g2s(w_smem + (size_t)ks * kResWSliceBytes, wsrc + (size_t)ks * kResN * kSliceK, kResWSliceBytes, w_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int m_tile = first + it * stride;
+        for (int ks = 0; ks < t.n_ks; ++ks) {
+          mbar_wait(&a_empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&a_full[stage], (uint32_t)kABytes);
+          tma_load_2d(a_smem + (size_t)stage * kABytes, &tmA, ks * kSliceK, m_tile * kTileM, &a_full[stage]);
+          if (++stage == kResStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kResMmaWarp) {
+    if (lane == 0 && my_items > 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, kResN);
+      mbar_wait(w_full, 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kMaxN);
+        for (int ks = 0; ks < t.n_ks; ++ks) {
+          mbar_wait(&a_full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(a_smem + (size_t)stage * kABytes));
+          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(w_smem + (size_t)ks * kResWSliceBytes));
+#pragma unroll
+          for (int k = 0; k < kSliceK / 16; ++k)
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&a_empty[stage]);
+          if (++stage == kResStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // epilogue: warp w drains TMEM lane quarter w % 4 (hardware rule); the three warps of a quarter take the
+    // 32-column chunks {i, i + 3} (i = w / 4).  Bias, activation, fp16, shared staging, 64-byte row stores.
+    const int q = warp & 3, third = warp >> 2;
+    unsigned char* stg = epi_stage + (size_t)warp * kEpiWarpBytes;
+    const int n0 = pass * kResN;
+    for (int it = 0; it < my_items; ++it) {
+      const int m_tile = first + it * stride;
+      const int buf = it & 1;
+      const int row_base = m_tile * kTileM + q * 32;
+      mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kMaxN);
+      for (int c0 = third * 32; c0 < kResN; c0 += 96) {
+        uint32_t v[32];
+        tmem_ld32_async(taddr0 + (uint32_t)c0, v);
+        tmem_ld_wait(v);
+        const float4* b4 = reinterpret_cast<const float4*>(t.bias + n0 + c0);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 bb = __ldg(b4 + 2 * jj + h2);
+            const int e = 8 * jj + 4 * h2;
+            float x0 = __uint_as_float(v[e]) + bb.x, x1 = __uint_as_float(v[e + 1]) + bb.y;
+            float x2 = __uint_as_float(v[e + 2]) + bb.z, x3 = __uint_as_float(v[e + 3]) + bb.w;
+            if (t.act == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+            packed[2 * h2] = pack_half2(x0, x1);
+            packed[2 * h2 + 1] = pack_half2(x2, x3);
+          }
+          *reinterpret_cast<uint4*>(stg + (uint32_t)lane * kEpiPitch + (uint32_t)jj * 16u) =
+              make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + (uint32_t)rr * kEpiPitch + (uint32_t)ch * 16u);
+          const int grow = row_base + rr;
+          if (grow < t.T) *reinterpret_cast<uint4*>(t.Y + (size_t)grow * t.N + n0 + c0 + ch * 8) = w;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kResMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -669,23 +847,78 @@ using namespace rl;
 extern "C" size_t rl_xenc_linear_image_bytes(int N, int K) {
   const int n_ks = (K + kSliceK - 1) / kSliceK;
   const int n_pad = (N + 15) / 16 * 16;
-  return (size_t)((n_pad + kMaxN - 1) / kMaxN) * kMaxN * n_ks * kSliceK * sizeof(__half);
+  const int pw = pass_width(N, K);
+  return (size_t)((n_pad + pw - 1) / pw) * pw * n_ks * kSliceK * sizeof(__half);
 }
 
 extern "C" int rl_xenc_pack_linear(const float* W, int N, int K, void* image, void* stream) {
   RL_REQUIRE(W && image && N > 0 && K > 0, RL_EINVAL, "rl_xenc_pack_linear: bad arguments");
   RL_REQUIRE(N % 16 == 0 && K % 8 == 0, RL_EUNSUPPORTED, "rl_xenc_pack_linear: N %% 16 and K %% 8 must be 0");
   RL_CUDA_CHECK(cudaMemsetAsync(image, 0, rl_xenc_linear_image_bytes(N, K), (cudaStream_t)stream));
-  pack_linear_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(W, N, K, reinterpret_cast<__half*>(image));
+  pack_linear_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(W, N, K, pass_width(N, K), reinterpret_cast<__half*>(image));
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int launch_linear_resident(const __half* X, const void* img, const float* bias, __half* Y, int T, int N, int K, int act,
+                                  int sm_count, cudaStream_t stream) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  RL_REQUIRE(enc != nullptr, RL_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  RL_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (K * 2) % 16 == 0, RL_EINVAL, "resident linear: X must be 16-byte aligned");
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)T};          // innermost first
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(__half)};        // bytes between token rows
+  const cuuint32_t box[2] = {(cuuint32_t)kSliceK, (cuuint32_t)kTileM};   // 64 halves (128 B, one swizzle row) x 128 tokens
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(X), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RL_REQUIRE(r == CUDA_SUCCESS, RL_ECUDA, "cuTensorMapEncodeTiled failed (%d) for X[%d, %d]", (int)r, T, K);
+  LinArgs t;
+  t.X = X; t.img = reinterpret_cast<const __half*>(img); t.bias = bias; t.Y = Y; t.T = T; t.N = N; t.K = K; t.act = act;
+  t.n_pass = N / kResN;
+  t.n_ks = K / kSliceK;
+  t.stages = kResStages;
+  t.cp_async = 0;
+  t.pw = kResN;
+  const size_t smem = (size_t)t.n_ks * kResWSliceBytes + (size_t)kResStages * kABytes + kBarBytes + kResEpiBytes + 1024;
+  RL_REQUIRE(smem <= 227 * 1024, RL_EUNSUPPORTED, "resident linear: %zu bytes of shared memory", smem);
+  RL_CUDA_CHECK(cudaFuncSetAttribute(linear_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int m_tiles = (T + kTileM - 1) / kTileM;
+  int per_pass = sm_count / t.n_pass;
+  if (per_pass < 1) per_pass = 1;
+  if (per_pass > m_tiles) per_pass = m_tiles;
+  linear_wres_kernel<<<t.n_pass * per_pass, kResThreads, smem, stream>>>(tm, t);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }
 
 static int launch_linear(const __half* X, const void* img, const float* bias, __half* Y, int T, int N, int K, int act,
                          int sm_count, cudaStream_t stream) {
+  // RL_XENC_RESIDENT=0 forces the streaming kernel (A/B switch; the image layout follows pass_width()).
+  static const bool resident_ok = []() { const char* e = getenv("RL_XENC_RESIDENT"); return e == nullptr || atoi(e) != 0; }();
+  if (use_resident(N, K)) {
+    if (resident_ok) return launch_linear_resident(X, img, bias, Y, T, N, K, act, sm_count, stream);
+  }
   LinArgs t;
   t.X = X; t.img = reinterpret_cast<const __half*>(img); t.bias = bias; t.Y = Y; t.T = T; t.N = N; t.K = K; t.act = act;
-  t.n_pass = (N + kMaxN - 1) / kMaxN;
+  t.pw = pass_width(N, K);
+  t.n_pass = (N + t.pw - 1) / t.pw;
   t.n_ks = (K + kSliceK - 1) / kSliceK;
   // cp.async activation loader (every free smem stage in flight, no registers held) is the default: bit-identical
   // outputs, 352 -> 309 us for the four GEMMs of a layer (profiles/r01_linear_loader_ab.json); RL_XENC_CPASYNC=0

@@ -147,9 +147,9 @@ def test_large_clustered(rl):
     from synth_torch import clustered_corpus_torch, queries_near_rows
 
     vecs, d, B, k, num_hits = 12, 1024, 256, 100, 400
-    E, cl = clustered_corpus_torch(BIG_ROWS, d, seed=4, device="cuda")
+    E, cl = clustered_corpus_torch(BIG_ROWS, d, seed=4, device="cuda", mean_cluster=1536, max_cluster=8192)
     sizes = np.bincount(cl[cl >= 0])
-    big_tight = np.nonzero((sizes >= 3000) & (np.arange(len(sizes)) % 4 <= 1))[0]   # spreads 0.02 / 0.05
+    big_tight = np.nonzero((sizes >= 4500) & (np.arange(len(sizes)) % 4 <= 1))[0]   # spreads 0.02 / 0.05
     assert len(big_tight) >= 4
     rng = np.random.default_rng(5)
     n_near = B - B // 4
@@ -170,6 +170,31 @@ def test_large_clustered(rl):
         assert st["survivors_max"] > 4096, "the generator must exercise the streaming survivor path"
         assert exact >= len(check) - 2
         del idx
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "l2"])
+def test_several_query_groups_per_tile(rl, metric):
+    """B > 256 (BASELINE configs[2] runs B = 1024): the scan walks every corpus tile once per group of 256
+    queries inside ONE launch; 600 queries = two full groups and a ragged third."""
+    from synth_torch import gaussian_corpus_torch, host_blocks, queries_near_rows
+
+    vecs, d, B, k = 4, 256, 600, 20
+    E = gaussian_corpus_torch(60_000 * vecs, d, seed=7, device="cuda")
+    if metric != "cosine":
+        E *= 1.5
+    idx = rl.CorpusIndex(E, vecs_per_chunk=vecs)
+    Q = queries_near_rows(E, B, seed=8)
+    cfg = rl.RAGLiteConfig(reranker=None, vector_search_distance_metric=metric)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=k, config=cfg, index=idx)
+    st = idx.scan_stats()
+    check = list(range(0, B, 7))
+    lists = ovs.topn_rows_blocked(host_blocks(E), Q[check].cpu().numpy(), 80 + 8, metric, f32_ties=True)
+    exact = _compare(lists, vecs, ids, sims, counts, k, 80, which=check)
+    _record(f"multi_group_{metric}", {"checked": len(check), "exact": exact, **st})
+    assert st["algo"] == 2 and exact >= len(check) - 2
+    ids2, sims2, counts2 = rl.vector_search_batch(Q[256:512], num_results=k, config=cfg, index=idx)   # one group, same queries
+    assert np.array_equal(ids2, ids[256:512]) and np.array_equal(counts2, counts[256:512])
+    assert np.allclose(sims2, sims[256:512], atol=0, equal_nan=True)
 
 
 def test_concurrent_searches_from_threads(rl):
