@@ -59,6 +59,7 @@ struct TcArgs {
   int nq;                 // padded #queries of a FULL group (multiple of 16; kMaxQ when n_groups > 1)
   int n_groups;           // query groups of kMaxQ walked per corpus tile (B <= n_groups * kMaxQ)
   int nq_last;            // padded #queries of the last group
+  int par_groups;         // > 1: group-parallel -- CTA c serves query group c % par_groups of the tiles of lane c / par_groups
   int n_ks;               // K slices
   int stages;
   int tmem_cols;          // allocated TMEM columns (power of two >= 2 * buf_cols)
@@ -106,7 +107,28 @@ __host__ __device__ inline uint32_t tail_bytes(int n_groups) {
 template <int METRIC, bool PAIR, bool EF16>
 __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
-  const ScanArgs& a = t.a;
+  // Group-parallel mode (B > 256, the default): the CTAs of a "lane" -- par_groups consecutive CTAs -- walk the
+  // SAME corpus tiles at the same time, one 256-query group each.  The first of them pulls a tile in from
+  // HBM, the others find it in L2 microseconds later, so HBM sees the corpus once; every CTA keeps the
+  // single-group shared-memory state.  (Walking the groups one after the other inside a CTA -- n_groups > 1 --
+  // puts a 512 KB x 148 = 76 MB reuse distance between the passes over a tile: the re-reads then miss L2.)
+  const int P = t.par_groups > 1 ? t.par_groups : 1;
+  const int pg = P > 1 ? (int)((PAIR ? blockIdx.x >> 1 : blockIdx.x) % (unsigned)P) : 0;
+  ScanArgs a = t.a;
+  const float* q_scale_g = t.q_scale;
+  const __half* qimg_g = t.qimg;
+  int nqF = t.nq, nqL = t.nq_last;       // padded width of a full group / of the last group this CTA serves
+  if (P > 1) {
+    const int q0p = pg * kMaxQ;
+    a.B = min(kMaxQ, t.a.B - q0p);
+    a.thr += q0p; a.cand_cnt += q0p; a.eps += q0p; a.hist_inv_w += q0p; a.q_inv_norm += q0p;
+    a.dump += (size_t)q0p * a.n_sample_rows;
+    a.cand += (size_t)q0p * a.cap;
+    a.ghist += (size_t)q0p * kHistBins;
+    q_scale_g += q0p;
+    qimg_g += (size_t)pg * t.n_ks * kMaxQ * kSliceK;
+    nqF = nqL = (pg == P - 1) ? t.nq_last : t.nq;
+  }
   // 1024-byte alignment for the 128B-swizzled tiles.
   // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -141,8 +163,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   // `rank` of the cluster takes ordinal 2 * unit + rank; a missing second block is an empty tile).
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int64_t n_tiles = PAIR ? (a.n_mode_blocks + 1) / 2 : a.n_mode_blocks;
-  const int64_t first = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-  const int64_t stride = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t first = (PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x) / P;
+  const int64_t stride = (PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x) / P;
   const int64_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
   auto ord_of = [&](int64_t tile) -> int64_t {
     const int64_t unit = first + tile * stride;
@@ -167,7 +189,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   }
   for (int i = threadIdx.x; i < QT; i += blockDim.x) {
     s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
-    s.cs[i] = (i < a.B) ? t.q_scale[i] : 0.f;
+    s.cs[i] = (i < a.B) ? q_scale_g[i] : 0.f;
     s.cnt[i] = 0;
     if (!multi) {
       s.thr0[i] = s.thr[i];
@@ -223,7 +245,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int pf_ks = 0, pf_rows = 0;
     const unsigned char* pf_ptr = nullptr;
     auto pf_set_tile = [&]() {   // only the first group's pass over a tile comes from HBM
-      if (pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
+      if (pg == 0 && pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
         const int64_t blk = mode_block_index(a, ord_of(pf_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         pf_rows = rem < kTileM ? (int)rem : kTileM;
@@ -326,7 +348,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     int pf_ks = 0, pf_rows = 0;
     const unsigned char* pf_ptr = nullptr;
     auto pf_set_tile = [&]() {   // only the first group's pass over a tile comes from HBM
-      if (pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
+      if (pg == 0 && pf_tile < v_tiles && pf_tile % G0 == 0 && ord_of(pf_tile / G0) < a.n_mode_blocks) {
         const int64_t blk = mode_block_index(a, ord_of(pf_tile / G0));
         const int64_t rem = a.n_rows - blk * kTileM;
         pf_rows = rem < kTileM ? (int)rem : kTileM;
@@ -446,9 +468,9 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       int ks = 0, stage = 0, g = 0;
       uint32_t phase = 0;
       for (int64_t item = 0; item < total_items; ++item) {
-        const uint32_t slice_bytes_q = (uint32_t)(g == G0 - 1 ? t.nq_last : t.nq) * 128u;   // one K slice of the group's queries
+        const uint32_t slice_bytes_q = (uint32_t)(g == G0 - 1 ? nqL : nqF) * 128u;   // one K slice of the group's queries
         const uint32_t qbytes = PAIR ? slice_bytes_q / 2 : slice_bytes_q;                    // PAIR: this CTA's half of them
-        const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(t.qimg) + (size_t)g * group_bytes +
+        const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(qimg_g) + (size_t)g * group_bytes +
                                     (PAIR ? (size_t)rank * qbytes : 0);
         mbar_wait(&s.empty[stage], phase ^ 1u);
         mbar_arrive_expect_tx(&s.full[stage], qbytes);
@@ -475,8 +497,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
         }
       }
     } else if (lane == 0) {
-      const uint32_t idesc_full = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq);
-      const uint32_t idesc_last = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, t.nq_last);
+      const uint32_t idesc_full = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, nqF);
+      const uint32_t idesc_last = make_idesc_f16(PAIR ? 2 * kTileM : kTileM, nqL);
       int stage = 0, g = 0;
       uint32_t phase = 0;
       for (int64_t tile = 0; tile < v_tiles; ++tile) {   // virtual tiles: (corpus tile, query group)
@@ -519,7 +541,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     for (int64_t vt = 0; vt < v_tiles; ++vt) {
       const int64_t tile = multi ? vt / G0 : vt;   // corpus tile
       const int q0 = g * kMaxQ;                    // first query slot of this group
-      const int nq_g = g == G0 - 1 ? t.nq_last : t.nq;
+      const int nq_g = g == G0 - 1 ? nqL : nqF;
       const int buf = (int)(vt & 1);
       const int64_t ord = ord_of(tile);
       const bool has_block = ord < a.n_mode_blocks;
@@ -763,14 +785,17 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
   if (a_in.n_mode_blocks == 0 || a_in.B == 0) return RL_OK;
   const int n_ks = (p->d + kSliceK - 1) / kSliceK;
   const int groups = (a_in.B + kMaxQ - 1) / kMaxQ;
-  // Up to kMaxGroups groups of 256 queries share one launch: the kernel walks every corpus tile once per
-  // group, back to back, so HBM sees the corpus once per launch (configs[2], B = 1024: one pass instead of
-  // four).  RL_TC_GROUPS=1 restores one launch per group (A/B switch).
+  // Up to kMaxGroups groups of 256 queries share one launch so that HBM sees the corpus once (configs[2],
+  // B = 1024).  Two ways to share (RL_TC_GROUPMODE): "par" (default) -- the CTAs of a lane walk the same
+  // tiles at the same time, one group each, and meet in L2; "seq" -- every CTA walks its tiles once per
+  // group, back to back (measured: the 76 MB reuse distance defeats L2, HBM still reads the corpus 3.5x).
+  // RL_TC_GROUPS=1 restores one launch per group.
   static const int max_groups = []() {
     const char* e = getenv("RL_TC_GROUPS");
     const int v = e ? atoi(e) : kMaxGroups;
     return v < 1 ? 1 : (v > kMaxGroups ? kMaxGroups : v);
   }();
+  static const bool seq_mode = []() { const char* e = getenv("RL_TC_GROUPMODE"); return e != nullptr && e[0] == 's'; }();
   for (int g0 = 0; g0 < groups; g0 += max_groups) {
     TcArgs t;
     t.a = a_in;
@@ -789,7 +814,9 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g0 * n_ks * kMaxQ * kSliceK;
     t.q_scale = q_scale + q0;
     t.row_stats = p->row_stats;
-    t.n_groups = ng;
+    const bool par = ng > 1 && !seq_mode && sm_count >= 2 * ng;
+    t.n_groups = par ? 1 : ng;
+    t.par_groups = par ? ng : 1;
     const int last_b = nb - (ng - 1) * kMaxQ;              // queries of the last group
     t.nq_last = (last_b + 15) / 16 * 16;
     t.nq = ng > 1 ? kMaxQ : t.nq_last;                     // a full group (the only group when ng == 1)
@@ -804,12 +831,12 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     static const int pair_env = []() { const char* e = getenv("RL_TC_PAIR"); return e ? atoi(e) : 0; }();
     const bool pair = pair_env == 1 && t.nq % 32 == 0 && t.nq_last % 32 == 0 && t.nq_last >= 64 && a_in.n_mode_blocks >= 2 &&
                       sm_count >= 2;
-    const uint32_t avail = kSmemBudget - 1024 - tail_bytes(ng);
+    const uint32_t avail = kSmemBudget - 1024 - tail_bytes(t.n_groups);
     int stages = (int)(avail / stage_bytes(pair ? t.nq / 2 : t.nq));
     if (stages > kMaxStages) stages = kMaxStages;
     RL_REQUIRE(stages >= 2, RL_EUNSUPPORTED, "tcgen05 scan: not enough shared memory for 2 stages");
     t.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes(pair ? t.nq / 2 : t.nq) + tail_bytes(ng) + 1024;
+    const size_t smem = (size_t)stages * stage_bytes(pair ? t.nq / 2 : t.nq) + tail_bytes(t.n_groups) + 1024;
     RL_REQUIRE(p->row_stats != nullptr, RL_EINVAL, "tcgen05 scan needs row_stats");
     auto launch = [&](auto kernel, bool is_pair) -> int {
       RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -817,13 +844,15 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
       cudaLaunchAttribute attr[1];
       if (is_pair) {
         const int64_t n_pairs = (a_in.n_mode_blocks + 1) / 2;
-        const int clusters = (int)(n_pairs < sm_count / 2 ? n_pairs : sm_count / 2);
+        const int units = sm_count / 2 / t.par_groups;                  // lanes of par_groups clusters each
+        const int clusters = (int)(n_pairs < units ? n_pairs : units) * t.par_groups;
         cfg.gridDim = dim3((unsigned)(2 * clusters));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
       } else {
-        cfg.gridDim = dim3((unsigned)(a_in.n_mode_blocks < sm_count ? a_in.n_mode_blocks : sm_count));
+        const int lanes = sm_count / t.par_groups;
+        cfg.gridDim = dim3((unsigned)((a_in.n_mode_blocks < lanes ? a_in.n_mode_blocks : lanes) * t.par_groups));
       }
       cfg.blockDim = dim3(kThreads);
       cfg.dynamicSmemBytes = smem;

@@ -911,7 +911,8 @@ static int launch_linear_resident(const __half* X, const void* img, const float*
 static int launch_linear(const __half* X, const void* img, const float* bias, __half* Y, int T, int N, int K, int act,
                          int sm_count, cudaStream_t stream) {
   // RL_XENC_RESIDENT=0 forces the streaming kernel (A/B switch; the image layout follows pass_width()).
-  static const bool resident_ok = []() { const char* e = getenv("RL_XENC_RESIDENT"); return e == nullptr || atoi(e) != 0; }();
+  const char* res_env = getenv("RL_XENC_RESIDENT");   // read per launch: tools/time_linear.py A/Bs it in one process
+  const bool resident_ok = res_env == nullptr || atoi(res_env) != 0;
   if (use_resident(N, K)) {
     if (resident_ok) return launch_linear_resident(X, img, bias, Y, T, N, K, act, sm_count, stream);
   }

@@ -20,12 +20,13 @@ for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
         cur = demangle(m.group(1))
-        cur = re.sub(r"\(.*", "", cur).replace("rl::(anonymous namespace)::", "").replace("rl::", "")
+        cur = cur.replace("(anonymous namespace)::", "").replace("rl::", "").replace("void ", "")
+        cur = re.sub(r"\(.*", "", cur)
         per[cur] = Counter()
         continue
     if cur is None:
         continue
-    m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m:
         op = m.group(1)
         per[cur]["_total"] += 1

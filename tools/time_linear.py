@@ -1,5 +1,6 @@
-"""A/B of the cross-encoder linear kernel's activation loader (register ring vs RL_XENC_CPASYNC=1):
-parity of every GEMM shape against torch, then CUDA-event timing of back-to-back launches."""
+"""A/B of the cross-encoder linear kernels: weight-resident + TMA tensor-map loader (default for K <= 384),
+streaming kernel with the cp.async loader, streaming kernel with the register-ring loader.  Parity of every
+GEMM shape against torch (incl. a ragged token count), then CUDA-event timing of back-to-back launches."""
 import json
 import os
 import sys
@@ -13,7 +14,7 @@ from raglite_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 g = torch.Generator().manual_seed(0)
-T = 51200
+T = 51200 + 77   # ragged: the last token tile is partial
 shapes = [("qkv", 1152, 384, 0), ("out", 384, 384, 0), ("ffn_up", 1536, 384, 1), ("ffn_down", 384, 1536, 0)]
 out = {}
 s = torch.cuda.current_stream().cuda_stream
@@ -27,8 +28,8 @@ for name, N, K, act in shapes:
     if act:
         ref = torch.nn.functional.gelu(ref)
     Y = torch.empty((T, N), dtype=torch.float16, device="cuda")
-    for mode in ("0", "1"):
-        os.environ["RL_XENC_CPASYNC"] = mode
+    for mode, (res, cpa) in {"resident": ("1", "1"), "stream_cpasync": ("0", "1"), "stream_ring": ("0", "0")}.items():
+        os.environ["RL_XENC_RESIDENT"], os.environ["RL_XENC_CPASYNC"] = res, cpa
         Y.zero_()
         assert lib.rl_xenc_linear(X.data_ptr(), img.data_ptr(), b.data_ptr(), Y.data_ptr(), T, N, K, act, s) == 0, lib.rl_last_error()
         torch.cuda.synchronize()
@@ -44,6 +45,6 @@ for name, N, K, act in shapes:
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
-        out[f"{name}_mode{mode}"] = {"us": round(us, 1), "tflops": round(2.0 * T * N * K / us / 1e6, 1), "max_err": err,
+        out[f"{name}_{mode}"] = {"us": round(us, 1), "tflops": round(2.0 * T * N * K / us / 1e6, 1), "max_err": err,
                                      "tail_err": tail_err}
 print(json.dumps(out))
