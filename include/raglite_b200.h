@@ -43,6 +43,8 @@ extern "C" {
 /* rl_maxsim_topk flags. */
 #define RL_FLAG_REUSE_THRESHOLDS 1u /* skip the sample pass; use thresholds left in the workspace */
 #define RL_FLAG_TIME_KERNELS 2u     /* record CUDA events around each stage (see rl_maxsim_kernel_times) */
+#define RL_FLAG_COUNT_UNFILTERED 4u /* also count, per query, the rows that pass the emission threshold but are masked
+                                       out by row_allowed (and alive per row_alive): rl_maxsim_unfiltered_bound */
 
 /* Per-query status bits written by rl_maxsim_topk. */
 #define RL_STATUS_CAND_OVERFLOW 1 /* candidate list overflowed: call again with REUSE_THRESHOLDS */
@@ -128,6 +130,8 @@ typedef struct rl_scan_params {
   int32_t cand_cap;      /* 0 = auto */
   int32_t e_dtype;       /* storage of E: 0 = float32, 1 = float16 (E then points to IEEE binary16; needs
                             RL_ALGO_TCGEN05, d % 8 == 0 and rows that need no per-row scaling) */
+  const uint8_t* row_alive; /* optional uint8[n_rows] (NULL = all): rows that exist at all -- the tombstone mask without
+                            the metadata filter (only read with RL_FLAG_COUNT_UNFILTERED) */
 } rl_scan_params;
 
 size_t rl_maxsim_workspace_bytes(const rl_scan_params* p);
@@ -148,6 +152,16 @@ typedef struct rl_scan_stats {
   int64_t survivors_max; /* largest per-query survivor count (> RL_MAX_SURVIVORS: that query took the streaming path) */
 } rl_scan_stats;
 int rl_maxsim_stats(const rl_scan_params* p, const void* workspace, rl_scan_stats* out, void* stream);
+
+/* Fused bound for the rank-then-filter metadata branch (_search.py:122-143).  After an rl_maxsim_topk call made
+ * with RL_FLAG_COUNT_UNFILTERED on a FILTERED scan (row_allowed set), bound[b] (device int64 [B]) is an UPPER bound
+ * of the number of live rows of the shard -- filtered or not -- that are at least as near to query b as the worst
+ * of its num_hits filtered hits: every emission threshold the scan ever used lies at or below that hit's key, so
+ * the rows counted against the thresholds (allowed ones = the candidate count, masked ones = the extra counter)
+ * plus the whole sample are a superset.  bound <= 1 000 000 proves that the filter-first answer is also the
+ * rank-then-filter answer, without the second pass over the corpus rl_maxsim_count_at_least needs.  Returns
+ * RL_EUNSUPPORTED when the last call did not count (fp32 scan, flag not set). */
+int rl_maxsim_unfiltered_bound(const rl_scan_params* p, const void* workspace, int64_t* bound, void* stream);
 
 /* Rank probe for the reference's rank-then-filter metadata branch (_search.py:122-143, which keeps the
  * 1 000 000 nearest vectors before it applies the filter): counts[b] = number of rows of the shard

@@ -31,7 +31,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import RL_ALGO, RL_FLAG_REUSE_THRESHOLDS, RL_METRIC, RL_STATUS_CAND_OVERFLOW, ScanParams, ScanStats, check
+from ._lib import (RL_ALGO, RL_FLAG_COUNT_UNFILTERED, RL_FLAG_REUSE_THRESHOLDS, RL_METRIC, RL_STATUS_CAND_OVERFLOW, ScanParams,
+                   ScanStats, check)
 from ._typing import ChunkId
 
 
@@ -600,6 +601,8 @@ class CorpusIndex:
             if self._alive is not None and not mask_has_tombstones:  # tombstoned rows are masked like a metadata filter
                 row_allowed = self._alive if row_allowed is None else (row_allowed & self._alive)
             p = self._params(Q, k, num_hits, metric, algo, row_allowed, flags, sample_stride, cand_cap)
+            if flags & RL_FLAG_COUNT_UNFILTERED:
+                p.row_alive = _ptr(self._alive)
             need = int(self.lib.rl_maxsim_workspace_bytes(C.byref(p)))
             if need == 0 and B > 0:
                 raise _lib.RagliteB200Error("rl_maxsim_workspace_bytes: " + self.lib.rl_last_error().decode())
@@ -635,6 +638,17 @@ class CorpusIndex:
             check(self.lib.rl_maxsim_count_at_least(C.byref(p), _ptr(floor), int(bound), _ptr(counts), _ptr(ws),
                                                     ws.numel(), _stream()), "rl_maxsim_count_at_least")
         return counts
+
+    def unfiltered_bound(self) -> torch.Tensor:
+        """``rl_maxsim_unfiltered_bound`` of the last scan (made with ``RL_FLAG_COUNT_UNFILTERED``): per query an
+        upper bound of the live rows of this shard at least as near as the worst filtered hit; -1 where the
+        scan did not count (float32 kernel).  int64 ``[B]`` on the device, no synchronisation."""
+        p = self.last_params
+        out = torch.empty(int(p.B), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rl_maxsim_unfiltered_bound(C.byref(p), _ptr(self.last_ws), _ptr(out), _stream()),
+                  "rl_maxsim_unfiltered_bound")
+        return out
 
     def sum_over_shards(self, x: torch.Tensor) -> torch.Tensor:
         """A single shard is the whole corpus (``ShardedIndex`` all-reduces)."""
@@ -713,8 +727,8 @@ class CorpusIndex:
         return self.chunk_ids[local] if self.chunk_ids is not None else str(int(global_chunk))
 
     # ---- results to the host in one copy ------------------------------------------------------------------
-    def to_host(self, sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor
-                ) -> tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    def to_host(self, sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor,
+                extra: torch.Tensor | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray, int] | tuple:
         """One device->host copy (pinned staging buffer) of a merged result plus the OR of the status words,
         then ONE stream synchronisation -- the only host sync of a search."""
         B, k = int(sim.shape[0]), int(sim.shape[1])
@@ -722,6 +736,8 @@ class CorpusIndex:
         st_any = st_any.max().reshape(1) if st_any.numel() else torch.zeros(1, dtype=torch.int32, device=sim.device)
         parts = [chunk.contiguous().view(torch.uint8).reshape(-1), sim.contiguous().view(torch.uint8).reshape(-1),
                  count.to(torch.int32).contiguous().view(torch.uint8).reshape(-1), st_any.view(torch.uint8).reshape(-1)]
+        if extra is not None:   # an int64 [B] vector rides along (e.g. the rank-then-filter bound)
+            parts.insert(0, extra.to(torch.int64).contiguous().view(torch.uint8).reshape(-1))
         dev = torch.cat(parts)
         n = int(dev.numel())
         host = self._pinned.get(n)
@@ -733,11 +749,16 @@ class CorpusIndex:
         host.copy_(dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         raw = host.numpy()
+        ext = None
+        if extra is not None:
+            ext = raw[: extra.numel() * 8].view(np.int64).copy()
+            raw = raw[extra.numel() * 8:]
         n8, n4 = B * k * 8, B * k * 4
         ids = raw[:n8].view(np.int64).reshape(B, k).copy()
         sims = raw[n8:n8 + n4].view(np.float32).reshape(B, k).copy()
         counts = raw[n8 + n4:n8 + n4 + B * 4].view(np.int32).copy()
-        return ids, sims, counts, int(raw[n8 + n4 + B * 4:].view(np.int32)[0])
+        st = int(raw[n8 + n4 + B * 4:].view(np.int32)[0])
+        return (ids, sims, counts, st) if extra is None else (ids, sims, counts, st, ext)
 
 
 def next_overflow_attempt(local: "CorpusIndex", attempt: int, cap: int, base_flags: int) -> tuple[int, int]:
@@ -766,12 +787,25 @@ def search_to_host(  # noqa: PLR0913
     with local._lock, torch.cuda.device(local.device):
         mask = local.row_mask(chunk_ok)
         cap, flags = 0, 0
+        # Rank-then-filter branch (_search.py:122-143): first try to PROVE, from counters the filtered scan keeps
+        # anyway, that fewer than `limit` rows of the whole corpus are as near as the worst filtered hit -- then
+        # the filter-first answer is the answer and no second pass over the corpus is needed.
+        fused = rank_first_limit is not None and mask is not None
         for attempt in range(16):
             sim, chunk, count, status = index.search_pipeline(
                 Q, k=k, num_hits=num_hits, metric=metric, algo=algo, row_allowed=mask, mask_has_tombstones=True,
-                flags=flags, cand_cap=cap, rank_first_limit=rank_first_limit)
-            ids, sims, counts, st = local.to_host(sim, chunk, count, status)
+                flags=flags | (RL_FLAG_COUNT_UNFILTERED if fused else 0), cand_cap=cap,
+                rank_first_limit=None if fused else rank_first_limit)
+            if fused:
+                bound = index.sum_over_shards(local.unfiltered_bound().clamp(min=-1))
+                neg = index.sum_over_shards((local.unfiltered_bound() < 0).to(torch.int64))   # any shard that did not count
+                ids, sims, counts, st, ub = local.to_host(sim, chunk, count, status, torch.where(neg > 0, -1, bound))
+            else:
+                ids, sims, counts, st = local.to_host(sim, chunk, count, status)
             if not st & RL_STATUS_CAND_OVERFLOW:
+                if fused and (ub.min() < 0 or ub.max() > rank_first_limit):
+                    fused = False       # not provable from the counters: run the explicit rank probe
+                    continue
                 return ids, sims, counts
             cap, flags = next_overflow_attempt(local, attempt + 1, cap, 0)
     raise _lib.RagliteB200Error("candidate lists still overflow with a list as large as the shard")

@@ -16,13 +16,14 @@ RL_METRIC = {"cosine": 0, "dot": 1, "l2": 2}
 RL_ALGO = {"auto": 0, "fp32": 1, "tcgen05": 2}
 RL_FLAG_REUSE_THRESHOLDS = 1
 RL_FLAG_TIME_KERNELS = 2
+RL_FLAG_COUNT_UNFILTERED = 4
 RL_STATUS_CAND_OVERFLOW = 1
 RL_STATUS_TIE_OVERFLOW = 2
 RL_MAX_SURVIVORS = 4096   # finalize window (include/raglite_b200.h)
 
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
-    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_topk_merge_packed", "rl_hits_packed_bytes", "rl_row_mask",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_unfiltered_bound", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_topk_merge_packed", "rl_hits_packed_bytes", "rl_row_mask",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
@@ -37,6 +38,7 @@ class ScanParams(C.Structure):
         ("Q", C.c_void_p),
         ("B", C.c_int32), ("metric", C.c_int32), ("k", C.c_int32), ("num_hits", C.c_int32), ("algo", C.c_int32),
         ("flags", C.c_uint32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32), ("e_dtype", C.c_int32),
+        ("row_alive", C.c_void_p),
     ]
 
 
@@ -80,6 +82,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_maxsim_workspace_bytes.restype = C.c_size_t
     lib.rl_maxsim_topk.argtypes = [C.POINTER(ScanParams), vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.rl_maxsim_count_at_least.argtypes = [C.POINTER(ScanParams), vp, C.c_int, vp, vp, C.c_size_t, vp]
+    lib.rl_maxsim_unfiltered_bound.argtypes = [C.POINTER(ScanParams), vp, vp, vp]
     lib.rl_maxsim_stats.argtypes = [C.POINTER(ScanParams), vp, C.POINTER(ScanStats), vp]
     lib.rl_maxsim_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.rl_maxsim_release.argtypes = [vp]

@@ -133,6 +133,7 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   L->off_nsurv = take(B * 4);
   L->off_hist = take(B * kHistBins * 4);
   L->off_histw = take(B * 4);
+  L->off_cntall = take(B * 4);
   L->off_qimg = take(algo == RL_ALGO_TCGEN05 ? tcgen05_qimg_bytes(p->B, p->d) : 0);
   L->off_dump = take(B * (size_t)L->n_sample_rows * 4);
   L->off_cand = take(B * (size_t)L->cap * sizeof(Cand));
@@ -206,10 +207,12 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   int32_t* n_surv = reinterpret_cast<int32_t*>(ws + L.off_nsurv);
   int32_t* ghist = reinterpret_cast<int32_t*>(ws + L.off_hist);
   float* hist_inv_w = reinterpret_cast<float*>(ws + L.off_histw);
+  int32_t* cnt_all = reinterpret_cast<int32_t*>(ws + L.off_cntall);
   void* qimg = ws + L.off_qimg;
   float* dump = reinterpret_cast<float*>(ws + L.off_dump);
   Cand* cand = reinterpret_cast<Cand*>(ws + L.off_cand);
   const bool reuse = (p->flags & RL_FLAG_REUSE_THRESHOLDS) != 0;
+  const bool count_unf = (p->flags & RL_FLAG_COUNT_UNFILTERED) != 0 && p->row_allowed != nullptr && L.algo == RL_ALGO_TCGEN05;
   int launches = 0;
   cudaEvent_t* se = (p->flags & RL_FLAG_TIME_KERNELS) ? stage_events_for(workspace) : nullptr;
   auto mark = [&](int i) { if (se) cudaEventRecord(se[i], stream); };
@@ -217,6 +220,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
 
   RL_CUDA_CHECK(cudaMemsetAsync(cand_cnt, 0, (size_t)p->B * 4, stream));
   RL_CUDA_CHECK(cudaMemsetAsync(ghist, 0, (size_t)p->B * kHistBins * 4, stream));
+  if (count_unf) RL_CUDA_CHECK(cudaMemsetAsync(cnt_all, 0, (size_t)p->B * 4, stream));
   rc = launch_query_prep(p->Q, p->B, p->d, p->metric, L.algo, p->row_stats, q_sq, q_inv, eps, stream);
   if (rc != RL_OK) return rc;
   ++launches;
@@ -234,6 +238,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   a.d = p->d; a.B = p->B; a.metric = p->metric; a.S = L.S; a.cap = L.cap;
   a.ghist = ghist; a.eps = eps; a.hist_inv_w = hist_inv_w;
   a.sel_count = L.mode_sql ? p->num_hits : (p->k - 1) * p->max_vecs_per_chunk + 1;
+  a.row_alive = p->row_alive; a.cnt_all = count_unf ? cnt_all : nullptr;
 
   auto scan = [&](int dump_mode, int64_t n_mode_blocks) -> int {
     if (n_mode_blocks == 0) return RL_OK;
@@ -271,7 +276,7 @@ extern "C" int rl_maxsim_topk(const rl_scan_params* p, float* hit_sim, int64_t* 
   f.n_surv = n_surv; f.header = hdr; f.ld = p->ld; f.chunk_base = p->chunk_base; f.n_sample_rows = L.n_sample_rows;
   f.d = p->d; f.metric = p->metric; f.cap = L.cap; f.mode_sql = L.mode_sql;
   f.sel_k = L.mode_sql ? p->num_hits : (p->k - 1) * p->max_vecs_per_chunk + 1;
-  f.H = L.H; f.launches = launches + 1; f.S = L.S; f.algo = L.algo; f.e_f16 = p->e_dtype;
+  f.H = L.H; f.launches = launches + 1; f.S = L.S; f.algo = L.algo; f.e_f16 = p->e_dtype; f.counted_unfiltered = count_unf ? 1 : 0;
   rc = launch_finalize(f, p->B, stream);
   mark(5);
   return rc;
@@ -459,4 +464,28 @@ extern "C" int rl_topk_merge_packed(const void* packed, int64_t rank_stride_byte
   m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k; m.win = 0;
   m.chunk_rs = rank_stride_bytes / 8; m.sim_rs = rank_stride_bytes / 4; m.count_rs = rank_stride_bytes / 4;
   return launch_merge(m, (cudaStream_t)stream);
+}
+
+namespace rl {
+__global__ void unfiltered_bound_kernel(const Header* hdr, const int32_t* cand_cnt, const int32_t* cnt_all, int B,
+                                        int64_t* bound) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  // not counted (fp32 scan / flag not set): no bound
+  bound[b] = hdr->counted_unfiltered ? (int64_t)cand_cnt[b] + (int64_t)cnt_all[b] + hdr->n_sample_rows : (int64_t)-1;
+}
+}  // namespace rl
+
+extern "C" int rl_maxsim_unfiltered_bound(const rl_scan_params* p, const void* workspace, int64_t* bound, void* stream) {
+  RL_REQUIRE(p && workspace && bound, RL_EINVAL, "rl_maxsim_unfiltered_bound: null pointer");
+  Layout L;
+  int rc = make_layout(p, 148, &L);
+  if (rc != RL_OK) return rc;
+  if (p->B == 0) return RL_OK;
+  const unsigned char* ws = static_cast<const unsigned char*>(workspace);
+  unfiltered_bound_kernel<<<(p->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const Header*>(ws + L.off_hdr), reinterpret_cast<const int32_t*>(ws + L.off_cnt),
+      reinterpret_cast<const int32_t*>(ws + L.off_cntall), p->B, bound);
+  RL_CUDA_CHECK(cudaGetLastError());
+  return RL_OK;
 }

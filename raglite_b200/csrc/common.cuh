@@ -87,13 +87,14 @@ struct Layout {
   int b_pad;             // B rounded up to 16
   // byte offsets
   size_t off_hdr, off_dump, off_cand, off_cnt, off_thr, off_thr_out, off_eps, off_qinv, off_qsq,
-      off_qscale, off_qimg, off_nsurv, off_hist, off_histw, total;
+      off_qscale, off_qimg, off_nsurv, off_hist, off_histw, off_cntall, total;
 };
 int make_layout(const rl_scan_params* p, int sm_count, Layout* L);
 
 struct Header {  // first bytes of the workspace
   int32_t launches, sample_stride, cand_cap, algo;
   int64_t n_sample_rows;
+  int32_t counted_unfiltered, pad_;   // 1: off_cntall holds the counters of the last call
 };
 
 }  // namespace rl

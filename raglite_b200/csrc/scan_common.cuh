@@ -9,6 +9,8 @@ struct ScanArgs {
   const float* inv_norm;     // [n_rows]
   const float* sq_norm;      // [n_rows]
   const uint8_t* row_allowed;  // [n_rows] or null
+  const uint8_t* row_alive;    // [n_rows] or null: tombstones only (read when cnt_all is set)
+  int32_t* cnt_all;            // [B] or null: rows passing the threshold that row_allowed masks out
   const float* Q;            // [B, d] float32 (fp32 scan)
   const float* q_inv_norm;   // [B]
   const float* thr;          // [B] emission thresholds (EMIT mode)

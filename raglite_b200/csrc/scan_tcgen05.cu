@@ -122,6 +122,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
     const int q0p = pg * kMaxQ;
     a.B = min(kMaxQ, t.a.B - q0p);
     a.thr += q0p; a.cand_cnt += q0p; a.eps += q0p; a.hist_inv_w += q0p; a.q_inv_norm += q0p;
+    if (a.cnt_all != nullptr) a.cnt_all += q0p;
     a.dump += (size_t)q0p * a.n_sample_rows;
     a.cand += (size_t)q0p * a.cap;
     a.ghist += (size_t)q0p * kHistBins;
@@ -549,7 +550,13 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       const int r_in = q * 32 + lane;
       const int64_t row = blk * kTileM + r_in;
       bool valid = has_block && row < a.n_rows;
-      if (valid && a.row_allowed != nullptr) valid = a.row_allowed[row] != 0;
+      // rows the metadata filter masks out but that exist (not tombstoned): counted against the threshold when the
+      // caller asks for the rank-then-filter bound (rl_maxsim_unfiltered_bound)
+      bool masked_alive = false;
+      if (valid && a.row_allowed != nullptr) {
+        valid = a.row_allowed[row] != 0;
+        if (!valid && a.cnt_all != nullptr) masked_alive = a.row_alive == nullptr || a.row_alive[row] != 0;
+      }
       const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
       const float lane_scale = (METRIC == RL_METRIC_COSINE && cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
       mbar_wait(&s.tmem_full[buf], (uint32_t)((vt >> 1) & 1));
@@ -576,6 +583,14 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[q0 + c0 + j], bias);
             else key *= lane_scale;
             if (key >= s.thr[q0 + c0 + j]) mask |= 1u << j;
+          }
+          if (masked_alive) {   // (only with RL_FLAG_COUNT_UNFILTERED on a filtered scan)
+            uint32_t extra = mask;
+            while (extra != 0) {
+              const int j = __ffs(extra) - 1;
+              extra &= extra - 1;
+              atomicAdd(a.cnt_all + q0 + c0 + j, 1);
+            }
           }
           if (!valid) mask = 0;
           while (mask != 0) {  // rare: a few hits per tile; picks v[j] with a register select tree
@@ -811,6 +826,7 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.a.eps = a_in.eps + q0;
     t.a.hist_inv_w = a_in.hist_inv_w + q0;
     t.a.q_inv_norm = a_in.q_inv_norm + q0;
+    t.a.cnt_all = a_in.cnt_all ? a_in.cnt_all + q0 : nullptr;
     t.qimg = reinterpret_cast<const __half*>(qimg) + (size_t)g0 * n_ks * kMaxQ * kSliceK;
     t.q_scale = q_scale + q0;
     t.row_stats = p->row_stats;

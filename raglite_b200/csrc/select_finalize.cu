@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
     f.header->cand_cap = f.cap;
     f.header->algo = f.algo;
     f.header->n_sample_rows = f.n_sample_rows;
+    f.header->counted_unfiltered = f.counted_unfiltered;
   }
   const int cnt = f.cand_cnt[b];
   const int n = min(cnt, f.cap);

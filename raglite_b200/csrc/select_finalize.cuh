@@ -34,7 +34,7 @@ struct FinalizeArgs {
   int32_t* n_surv;            // [B]
   Header* header;
   int64_t ld, chunk_base, n_sample_rows;
-  int32_t d, metric, cap, mode_sql, sel_k, H, launches, S, algo, e_f16;
+  int32_t d, metric, cap, mode_sql, sel_k, H, launches, S, algo, e_f16, counted_unfiltered;
 };
 
 struct MergeArgs {

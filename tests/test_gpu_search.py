@@ -550,3 +550,38 @@ def test_metadata_rank_then_filter_branch(rl, monkeypatch):
     ids, sims, _ = ovs.vector_search_sql(E, off, Q[0], num_results=k, allowed_chunks=few, f64=True, filter_first_max=60,
                                          rank_first_limit=400)
     assert chunk[0, :count[0]].tolist() == ids.tolist() and len(ids) == 5
+
+
+def test_rank_then_filter_is_proven_without_a_second_pass(rl, monkeypatch):
+    """The usual rank-then-filter case (many rows match, the filtered hits are nowhere near the 1M-th nearest
+    row): counters the filtered scan keeps anyway (``rl_maxsim_unfiltered_bound``) prove that the filter-first
+    answer stands, so no counting pass over the corpus runs.  Constants scaled: 100_000 -> 1_000 matching rows,
+    1_000_000 -> 20_000 nearest vectors."""
+    import raglite_b200._search as S
+    from raglite_b200._index import CorpusIndex
+
+    monkeypatch.setattr(S, "FILTER_FIRST_MAX_ROWS", 1_000)
+    monkeypatch.setattr(S, "RANK_FIRST_LIMIT", 20_000)
+
+    def no_probe(*a, **k):
+        raise AssertionError("the explicit rank probe must not run here")
+
+    monkeypatch.setattr(CorpusIndex, "count_at_least", no_probe)
+    E, off = make_corpus(20_000, 3, 64, seed=330, fp16_round=True)
+    C = len(off) - 1
+    tagged = (np.arange(C) % 2 == 0)
+    idx = rl.CorpusIndex(E, off, chunk_ids=[str(c) for c in range(C)], chunk_metadata=[{"half": int(t)} for t in tagged])
+    idx.delete_chunks([str(c) for c in range(0, C, 10)])         # tombstones must not count as live rows
+    alive = np.arange(C) % 10 != 0
+    Q = make_queries(E, 12, seed=331)
+    cfg = rl.RAGLiteConfig(reranker=None)
+    chunk, sim, count = rl.vector_search_batch(Q, num_results=10, metadata_filter={"half": 1}, index=idx, config=cfg)
+    ub = idx.unfiltered_bound().cpu().numpy()
+    assert (ub > 0).all() and ub.max() <= 20_000
+    for b in range(len(Q)):
+        # the bound really is an upper bound of the live rows at least as near as the worst filtered hit
+        d = ovs.vector_distances_f64(E, Q[b], "cosine")
+        rows_ok = np.repeat(tagged & alive, np.diff(off))
+        worst = np.sort(d[rows_ok])[79]
+        assert ub[b] >= int((d[np.repeat(alive, np.diff(off))] <= worst).sum())
+        check_sql_semantics(E, off, Q[b], chunk[b, :count[b]], sim[b, :count[b]], k=10, allowed_chunks=tagged & alive)
