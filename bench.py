@@ -453,7 +453,7 @@ def run_pool(args: argparse.Namespace, w: dict) -> None:
         v = n * T_seg / dt
         print(json.dumps({"impl": "reference", "metric": "late-chunking pool token rows/sec", "value": v, "unit": "token rows/s",
                           "n_gpus": args.gpus, "steps": reps, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True,
-                          "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": w["desc"]},
                           "cpu_baseline": {"value": v, "unit": "token rows/s", "cores": 1, "kind": "port",
                                            "sample": f"{n} segments x {T_seg} x {d} (oracle.pool.late_chunk_pool, NumPy float64)"},
@@ -512,7 +512,7 @@ def run_pool(args: argparse.Namespace, w: dict) -> None:
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     ach = alg_bytes / (ms * 1e-3) / 1e9
     line = {"metric": "late-chunking pool token rows/sec", "value": T / (ms * 1e-3), "unit": "token rows/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "replicas only",
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "segments": n_seg, "token_rows": T, "pooled_rows": pooled_rows, "sentences": S, "dim": d,
                        "l2": "token matrix (%.1f GB) >> L2" % (T * d * 4 / 1e9)},
@@ -725,10 +725,21 @@ def main() -> None:  # noqa: PLR0915
     (ids, sims, counts), e2e_ms = timed_e2e()
     e2e_value = B / (e2e_ms * 1e-3) * norm
     filtered = None
+    probe_calls = {"n": 0}
+    if args.filtered:
+        _orig_count = type(local).count_at_least
+
+        def _counting(self, *a, **kw):  # noqa: ANN001, ANN002, ANN003, ANN202
+            probe_calls["n"] += 1
+            return _orig_count(self, *a, **kw)
+
+        type(local).count_at_least = _counting
     if args.filtered:   # both reference branches (_search.py:96-143), same batch, same API
         _, ms_rare = timed_e2e(metadata_filter={"rare": 1})      # <= 100k matching rows: filter, then rank
         _, ms_half = timed_e2e(metadata_filter={"half": 1})      # > 100k rows in a > 1M-vector table: rank, then filter
         filtered = {"filter_first_ms": ms_rare, "rank_then_filter_ms": ms_half, "unfiltered_ms": e2e_ms,
+                    "rank_probe_passes_over_the_corpus": probe_calls["n"], "matching_rows_rare": int(local.filter_chunks({"rare": [1]})[1]),
+                    "matching_rows_half": int(local.filter_chunks({"half": [1]})[1]),
                     "filter_first_vs_unfiltered": ms_rare / e2e_ms, "rank_then_filter_vs_unfiltered": ms_half / e2e_ms}
     clocks = sampler.stop(windows)
     clocks["windows"] = "timed device steps + timed e2e steps"

@@ -456,9 +456,22 @@ __global__ void __launch_bounds__(kResThreads, 1) linear_wres_kernel(const __gri
   } else {
     // epilogue: warp w drains TMEM lane quarter w % 4 (hardware rule); the three warps of a quarter take the
     // 32-column chunks {i, i + 3} (i = w / 4).  Bias, activation, fp16, shared staging, 64-byte row stores.
+    // The CTA's pass and each warp's two chunks never change, so the 64 bias values a thread needs live in
+    // registers for the whole launch (ncu: with a bias load in front of every add, the epilogue warps spent a
+    // third of their samples stalled on those loads and set the pace of the kernel).
     const int q = warp & 3, third = warp >> 2;
     unsigned char* stg = epi_stage + (size_t)warp * kEpiWarpBytes;
     const int n0 = pass * kResN;
+    float bias_r[2][32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float4* b4 = reinterpret_cast<const float4*>(t.bias + n0 + third * 32 + c * 96);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 bb = __ldg(b4 + e);
+        bias_r[c][4 * e] = bb.x; bias_r[c][4 * e + 1] = bb.y; bias_r[c][4 * e + 2] = bb.z; bias_r[c][4 * e + 3] = bb.w;
+      }
+    }
     for (int it = 0; it < my_items; ++it) {
       const int m_tile = first + it * stride;
       const int buf = it & 1;
@@ -466,20 +479,20 @@ __global__ void __launch_bounds__(kResThreads, 1) linear_wres_kernel(const __gri
       mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kMaxN);
-      for (int c0 = third * 32; c0 < kResN; c0 += 96) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = third * 32 + c * 96;
         uint32_t v[32];
         tmem_ld32_async(taddr0 + (uint32_t)c0, v);
         tmem_ld_wait(v);
-        const float4* b4 = reinterpret_cast<const float4*>(t.bias + n0 + c0);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           uint32_t packed[4];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 bb = __ldg(b4 + 2 * jj + h2);
             const int e = 8 * jj + 4 * h2;
-            float x0 = __uint_as_float(v[e]) + bb.x, x1 = __uint_as_float(v[e + 1]) + bb.y;
-            float x2 = __uint_as_float(v[e + 2]) + bb.z, x3 = __uint_as_float(v[e + 3]) + bb.w;
+            float x0 = __uint_as_float(v[e]) + bias_r[c][e], x1 = __uint_as_float(v[e + 1]) + bias_r[c][e + 1];
+            float x2 = __uint_as_float(v[e + 2]) + bias_r[c][e + 2], x3 = __uint_as_float(v[e + 3]) + bias_r[c][e + 3];
             if (t.act == 1) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
             packed[2 * h2] = pack_half2(x0, x1);
             packed[2 * h2 + 1] = pack_half2(x2, x3);
@@ -625,10 +638,14 @@ __device__ __forceinline__ void quad_transpose(uint32_t (&w)[4], int c) {
 
 template <bool QUAD>   // QUAD: 16-byte Q loads / context stores through a quad transpose; else (default) 4-byte fragment pieces
 __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
-                                                        int H, int n_heads, float scale_log2e, __half* __restrict__ ctx) {
+                                                        int H, int n_heads, float scale_log2e, __half* __restrict__ ctx,
+                                                        int len_lo, int len_hi) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   const int seq = blockIdx.x, head = blockIdx.y;
   const int t0 = cu[seq], L = cu[seq + 1] - t0;
+  // Length buckets: the launch's shared memory is sized for len_hi keys, so a launch for the short sequences
+  // keeps five CTAs per SM resident (41 KB each at 256 keys) instead of the three a 512-key allocation allows.
+  if (L <= len_lo || L > len_hi) return;
   const int Lp = (L + 63) / 64 * 64;
   __half* Ks = reinterpret_cast<__half*>(att_smem);
   __half* Vs = Ks + (size_t)Lp * kAttPitch;
@@ -988,6 +1005,10 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   RL_CUDA_CHECK(cudaGetLastError());
   const size_t att_smem = (size_t)((max_len + 63) / 64 * 64) * kAttPitch * 2 * sizeof(__half);
   RL_REQUIRE(att_smem <= 200 * 1024, RL_EUNSUPPORTED, "rl_xenc_score: max_len=%d too long for the attention kernel", max_len);
+  // Two launches when the batch holds long sequences: keys <= kAttShort with a small allocation (occupancy), the rest
+  // with the full one.  (ncu, round 2: a single launch sized by the longest sequence ran 3 CTAs = 12 warps per SM.)
+  constexpr int kAttShort = 256;
+  const size_t att_smem_short = (size_t)kAttShort * kAttPitch * 2 * sizeof(__half);
   // A/B switch for the Q loads / context stores.  Measured back to back on one B200 (262 k tokens per
   // layer): 4-byte fragment pieces 0.744 ms, 16-byte rows + quad transpose 1.100 ms -- so pieces are
   // the default and RL_XENC_ATT_QUAD=1 selects the transpose variant.
@@ -999,8 +1020,16 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     const rl_xenc_layer& L = w->layers[l];
     int rc = launch_linear(hidden, L.qkv_img, L.qkv_bias, qkv, T, 3 * H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
-    if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, att_smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
-    else attention_kernel<false><<<dim3(P, nh), 128, att_smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
+    auto attention = [&](size_t smem, int lo, int hi) {
+      if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
+      else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
+    };
+    if (max_len > kAttShort) {
+      attention(att_smem_short, 0, kAttShort);
+      attention(att_smem, kAttShort, max_len);
+    } else {
+      attention(att_smem, 0, max_len);
+    }
     RL_CUDA_CHECK(cudaGetLastError());
     rc = launch_linear(ctx, L.o_img, L.o_bias, tmp, T, H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
