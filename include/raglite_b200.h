@@ -130,6 +130,9 @@ typedef struct rl_scan_params {
   int32_t cand_cap;      /* 0 = auto */
   int32_t e_dtype;       /* storage of E: 0 = float32, 1 = float16 (E then points to IEEE binary16; needs
                             RL_ALGO_TCGEN05, d % 8 == 0 and rows that need no per-row scaling) */
+  int32_t rows_unit_scale; /* 1: the caller guarantees (from the rl_row_stats statistics: max 1/|e| <= 2, max |e_ij| <= 1024,
+                            no all-zero row -- true for normalised embeddings) that rows can enter the fp16 scan unscaled;
+                            lets the cosine scan use the two-tiles-per-query-slice kernel.  0: unknown (always valid) */
   const uint8_t* row_alive; /* optional uint8[n_rows] (NULL = all): rows that exist at all -- the tombstone mask without
                             the metadata filter (only read with RL_FLAG_COUNT_UNFILTERED) */
 } rl_scan_params;

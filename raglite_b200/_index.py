@@ -282,9 +282,15 @@ class CorpusIndex:
                        _stream()), "rl_row_stats")
 
     def _refresh_fp16_flag(self) -> None:
-        if self.storage == "fp16" and self.n_rows:
+        """Host copy of the decision the scan otherwise takes on the device: can rows enter the fp16 tensor-core
+        scan unscaled (norms >= 0.5, |x| <= 1024, no zero row -- normalised embeddings)?  Read once per index
+        change (build / append / compact synchronise anyway), passed as ``rl_scan_params.rows_unit_scale``."""
+        self._rows_unit_scale = False
+        if self.n_rows:
             st = self.stats.cpu().numpy()
-            self._fp16_cosine_ok = bool(0.0 < st[2] <= 2.0 and st[1] <= 1024.0 and st[3] == 0.0)
+            self._rows_unit_scale = bool(0.0 < st[2] <= 2.0 and st[1] <= 1024.0 and st[3] == 0.0)
+        if self.storage == "fp16":
+            self._fp16_cosine_ok = self._rows_unit_scale
 
     def reserve(self, n_rows: int) -> None:
         """Pre-size the row buffers (size HBM for the final corpus once instead of re-growing per flush)."""
@@ -566,6 +572,7 @@ class CorpusIndex:
         p.metric, p.k, p.num_hits, p.algo = RL_METRIC[metric], int(k), int(num_hits), RL_ALGO[algo]
         p.flags, p.sample_stride, p.cand_cap = flags, sample_stride, cand_cap
         p.e_dtype = 1 if self.storage == "fp16" else 0
+        p.rows_unit_scale = 1 if getattr(self, "_rows_unit_scale", False) else 0
         if self.storage == "fp16" and metric == "cosine" and not getattr(self, "_fp16_cosine_ok", True):
             raise ValueError("storage='fp16' with the cosine metric needs rows with norm >= 0.5 (normalised embeddings)")
         return p

@@ -38,7 +38,7 @@ class ScanParams(C.Structure):
         ("Q", C.c_void_p),
         ("B", C.c_int32), ("metric", C.c_int32), ("k", C.c_int32), ("num_hits", C.c_int32), ("algo", C.c_int32),
         ("flags", C.c_uint32), ("sample_stride", C.c_int32), ("cand_cap", C.c_int32), ("e_dtype", C.c_int32),
-        ("row_alive", C.c_void_p),
+        ("rows_unit_scale", C.c_int32), ("row_alive", C.c_void_p),
     ]
 
 

@@ -560,33 +560,68 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* __restrict
   }
 }
 
-// out = LayerNorm(x + res), one warp per token.
+// out = LayerNorm(x + res), one warp per token.  H % 128 == 0 (384 for MiniLM): a lane owns the columns
+// lane * 4 + 128 i, so every load / store instruction of the warp covers 256 contiguous bytes (8-byte pieces);
+// the first version moved 2 bytes per lane and instruction and ran at 3.5 TB/s.
+template <bool VEC>
 __global__ void __launch_bounds__(256) add_ln_kernel(const __half* __restrict__ xin, const __half* __restrict__ res,
                                                      const float* __restrict__ g, const float* __restrict__ bta, float eps,
                                                      int T, int H, __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= T) return;
-  float x[16];
+  float x[16];   // H <= 512
   float s = 0.f;
+  if (VEC) {
+    const uint2* xi = reinterpret_cast<const uint2*>(xin + (size_t)tok * H);
+    const uint2* ri = reinterpret_cast<const uint2*>(res + (size_t)tok * H);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = lane + 32 * i;
-    x[i] = c < H ? __half2float(xin[(size_t)tok * H + c]) + __half2float(res[(size_t)tok * H + c]) : 0.f;
-    s += x[i];
+    for (int i = 0; i < 4; ++i) {
+      if (i * 128 < H) {
+        const uint2 a = __ldg(xi + lane + 32 * i), r = __ldg(ri + lane + 32 * i);
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+        const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        x[4 * i] = a0.x + r0.x; x[4 * i + 1] = a0.y + r0.y; x[4 * i + 2] = a1.x + r1.x; x[4 * i + 3] = a1.y + r1.y;
+        s += (x[4 * i] + x[4 * i + 1]) + (x[4 * i + 2] + x[4 * i + 3]);
+      } else {
+        x[4 * i] = x[4 * i + 1] = x[4 * i + 2] = x[4 * i + 3] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < H ? __half2float(xin[(size_t)tok * H + c]) + __half2float(res[(size_t)tok * H + c]) : 0.f;
+      s += x[i];
+    }
   }
   const float mean = warp_sum_f(s) / (float)H;
   float var = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int c = lane + 32 * i;
+    const int c = VEC ? (i >> 2) * 128 : lane + 32 * i;   // (VEC: all four values of a piece are in or out together)
     if (c < H) var += (x[i] - mean) * (x[i] - mean);
   }
   const float rstd = rsqrtf(warp_sum_f(var) / (float)H + eps);
+  if (VEC) {
+    uint2* oo = reinterpret_cast<uint2*>(out + (size_t)tok * H);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = lane + 32 * i;
-    if (c < H) out[(size_t)tok * H + c] = __float2half_rn((x[i] - mean) * rstd * g[c] + bta[c]);
+    for (int i = 0; i < 4; ++i) {
+      if (i * 128 < H) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32 * i);
+        uint2 o;
+        o.x = pack_half2((x[4 * i] - mean) * rstd * gg.x + bb.x, (x[4 * i + 1] - mean) * rstd * gg.y + bb.y);
+        o.y = pack_half2((x[4 * i + 2] - mean) * rstd * gg.z + bb.z, (x[4 * i + 3] - mean) * rstd * gg.w + bb.w);
+        oo[lane + 32 * i] = o;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int c = lane + 32 * i;
+      if (c < H) out[(size_t)tok * H + c] = __float2half_rn((x[i] - mean) * rstd * g[c] + bta[c]);
+    }
   }
 }
 
@@ -998,6 +1033,7 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   __half* tmp = ctx + (size_t)T * H;
   __half* ffn = tmp + (size_t)T * H;
   const int tok_blocks = (T + 7) / 8;
+  const bool ln_vec = H % 128 == 0;   // (LayerNorm gamma / beta come from torch allocations: 16-byte aligned)
   embed_ln_kernel<<<tok_blocks, 256, 0, stream>>>(input_ids, type_ids, pos_ids, reinterpret_cast<const __half*>(w->word_emb),
                                                   reinterpret_cast<const __half*>(w->pos_emb),
                                                   reinterpret_cast<const __half*>(w->type_emb), w->emb_ln_g, w->emb_ln_b,
@@ -1024,7 +1060,11 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
       if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
       else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
     };
-    if (max_len > kAttShort) {
+    // Measured (ncu launch list, 51 k tokens per call, mean 200): two bucketed launches 86 + 64 us vs 141 us for one
+    // launch -- the long sequences carry 40 % of the L^2 work and gain nothing, the split adds a tail.  Off
+    // unless RL_XENC_ATT_BUCKETS=1.
+    static const bool buckets = []() { const char* e = getenv("RL_XENC_ATT_BUCKETS"); return e != nullptr && atoi(e) != 0; }();
+    if (buckets && max_len > kAttShort) {
       attention(att_smem_short, 0, kAttShort);
       attention(att_smem, kAttShort, max_len);
     } else {
@@ -1033,13 +1073,15 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     RL_CUDA_CHECK(cudaGetLastError());
     rc = launch_linear(ctx, L.o_img, L.o_bias, tmp, T, H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
-    add_ln_kernel<<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln1_g, L.ln1_b, w->ln_eps, T, H, hidden);
+    if (ln_vec) add_ln_kernel<true><<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln1_g, L.ln1_b, w->ln_eps, T, H, hidden);
+    else add_ln_kernel<false><<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln1_g, L.ln1_b, w->ln_eps, T, H, hidden);
     RL_CUDA_CHECK(cudaGetLastError());
     rc = launch_linear(hidden, L.up_img, L.up_bias, ffn, T, F, H, 1, sms, stream);
     if (rc != RL_OK) return rc;
     rc = launch_linear(ffn, L.down_img, L.down_bias, tmp, T, H, F, 0, sms, stream);
     if (rc != RL_OK) return rc;
-    add_ln_kernel<<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln2_g, L.ln2_b, w->ln_eps, T, H, hidden);
+    if (ln_vec) add_ln_kernel<true><<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln2_g, L.ln2_b, w->ln_eps, T, H, hidden);
+    else add_ln_kernel<false><<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln2_g, L.ln2_b, w->ln_eps, T, H, hidden);
     RL_CUDA_CHECK(cudaGetLastError());
   }
   cls_head_kernel<<<(P + 4 * kClsSeqs - 1) / (4 * kClsSeqs), 128, (size_t)4 * kClsSeqs * H * sizeof(float), stream>>>(
