@@ -736,21 +736,23 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
 // per step at B = 256, as much as the corpus itself.  This variant lets a CTA hold TWO corpus tiles per K slice
 // and issue both MMAs (M = 128 each) against ONE copy of the query slice: the L2 -> SM query stream halves.
 // The two accumulators take all 512 TMEM columns, so the epilogue of a tile pair does not overlap the MMAs
-// of the next pair; eight epilogue warps (four per tile) keep that window short, and the smem stages keep
-// filling while it lasts.  One group of <= 256 queries per CTA (B > 256 runs group-parallel lanes).
+// of the next pair (the smem stages keep filling while it lasts).  One group of <= 256 queries per CTA
+// (B > 256 runs group-parallel lanes).
 //
-// Stage: [A tile 0 16 KB | A tile 1 16 KB | query slice nq * 128 B].  Warps: 0-3 epilogue of tile 0, 4-7 of
-// tile 1 (TMEM lane quarter = warp % 4), 8 MMA issuer, 9 query producer, 10-17 corpus loaders.
-constexpr int kDualEpiWarps = 8;
-constexpr int kDualMmaWarp = 8;
-constexpr int kDualQWarp = 9;
-constexpr int kDualFirstLoader = 10;
-constexpr int kDualThreads = (kDualFirstLoader + kNumLoaderWarps) * 32;   // 576
+// Stage: [A tile 0 16 KB | A tile 1 16 KB | query slice nq * 128 B].  Same 14 warps as the single-tile kernel:
+// 0-3 epilogue (both tiles, one after the other; TMEM lane quarter = warp), 4 MMA issuer, 5 query producer,
+// 6-13 corpus loaders.  (Registers are allocated per 128 threads: a 576-thread block with four more epilogue
+// warps would be held to 96 registers per thread -- the probe in tools/probe_attrs.py shows it.)
+constexpr int kDualEpiWarps = kNumEpiWarps;
+constexpr int kDualMmaWarp = kMmaWarp;
+constexpr int kDualQWarp = kQWarp;
+constexpr int kDualFirstLoader = kFirstLoaderWarp;
+constexpr int kDualThreads = kThreads;   // 448
 __host__ __device__ inline uint32_t dual_stage_bytes(int nq) { return 2u * kABytes + (uint32_t)nq * 128u; }
-__device__ __forceinline__ void epi_bar_sync_dual() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync_dual() { epi_bar_sync(); }
 
 template <int METRIC, bool EF16>
-__global__ void __maxnreg__(112) scan_tcgen05_dual_kernel(const TcArgs t) {
+__global__ void __maxnreg__(128) scan_tcgen05_dual_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   const int P = t.par_groups > 1 ? t.par_groups : 1;
   const int pg = P > 1 ? (int)(blockIdx.x % (unsigned)P) : 0;
@@ -980,11 +982,14 @@ __global__ void __maxnreg__(112) scan_tcgen05_dual_kernel(const TcArgs t) {
       }
     }
   } else {
-    // ===== epilogue warps 0..7: tile half = warp / 4, TMEM lane quarter = warp % 4 =====
-    const int half = warp >> 2, q = warp & 3;
+    // ===== epilogue warps 0..3 (TMEM lane quarter = warp): tile 0, then tile 1 of the pair =====
+    const int q = warp;
     const bool cos_noscale = METRIC == RL_METRIC_COSINE;
     bool flushed_once = false;
     for (int64_t u = 0; u < my_units; ++u) {
+     mbar_wait(&s.tmem_full[0], (uint32_t)(u & 1));
+     tc_fence_after();
+     for (int half = 0; half < 2; ++half) {
       const int64_t ord = ord_of(u, half);
       const bool has_block = ord < a.n_mode_blocks;
       const int64_t blk = has_block ? mode_block_index(a, ord) : 0;
@@ -998,8 +1003,6 @@ __global__ void __maxnreg__(112) scan_tcgen05_dual_kernel(const TcArgs t) {
       }
       const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
       const float lane_scale = (cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
-      mbar_wait(&s.tmem_full[0], (uint32_t)(u & 1));
-      tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * t.buf_cols);
       for (int c0 = 0; c0 < nq; c0 += 32) {
         uint32_t v[32];
@@ -1054,9 +1057,10 @@ __global__ void __maxnreg__(112) scan_tcgen05_dual_kernel(const TcArgs t) {
           }
         }
       }
+     }   // half
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[0]);   // both accumulators are free once all 8 warps have arrived
+      if (lane == 0) mbar_arrive(&s.tmem_empty[0]);   // both accumulators are free once the 4 warps have arrived
       if (!a.dump_mode) {
         constexpr int NT = kDualEpiWarps * 32;
         const int et = threadIdx.x;  // 0..255
@@ -1320,6 +1324,30 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     if (rc != RL_OK) return rc;
   }
   return RL_OK;
+}
+
+// Debug probe: function attributes / occupancy of the scan kernels as the driver sees them.
+int debug_scan_kernel_attrs(int which, int* out) {
+  cudaFuncAttributes fa;
+  cudaError_t e = which == 0 ? cudaFuncGetAttributes(&fa, scan_tcgen05_kernel<0, false, false>)
+                             : (which == 1 ? cudaFuncGetAttributes(&fa, scan_tcgen05_dual_kernel<0, false>)
+                                           : cudaFuncGetAttributes(&fa, scan_tcgen05_dual_kernel<0, true>));
+  if (e != cudaSuccess) return (int)e;
+  out[0] = fa.numRegs; out[1] = fa.maxThreadsPerBlock; out[2] = (int)fa.sharedSizeBytes; out[3] = (int)fa.localSizeBytes;
+  out[4] = fa.maxDynamicSharedSizeBytes;
+  int nb = -1;
+  const size_t smem = 224448;
+  if (which >= 1) {
+    cudaFuncSetAttribute(which == 1 ? (const void*)scan_tcgen05_dual_kernel<0, false> : (const void*)scan_tcgen05_dual_kernel<0, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = which == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tcgen05_dual_kernel<0, false>, kDualThreads, smem)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tcgen05_dual_kernel<0, true>, kDualThreads, smem);
+  }
+  out[5] = nb; out[6] = (int)e;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  out[7] = prop.regsPerBlock; out[8] = prop.regsPerMultiprocessor; out[9] = (int)prop.sharedMemPerBlockOptin;
+  return 0;
 }
 
 }  // namespace rl
