@@ -292,6 +292,11 @@ class CorpusIndex:
         if self.storage == "fp16":
             self._fp16_cosine_ok = self._rows_unit_scale
 
+    @property
+    def rows_unit_scale(self) -> bool:
+        """True when every row can enter the fp16 scan unscaled (normalised embeddings): ``rl_scan_params.rows_unit_scale``."""
+        return bool(getattr(self, "_rows_unit_scale", False))
+
     def reserve(self, n_rows: int) -> None:
         """Pre-size the row buffers (size HBM for the final corpus once instead of re-growing per flush)."""
         with self._lock, torch.cuda.device(self.device):
