@@ -1286,8 +1286,12 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     int rc;
     const bool f16 = p->e_dtype == 1;
     // Two corpus tiles per query slice (halves the L2 -> SM query stream): one query group per CTA, rows that
-    // need no per-row scaling in the loader.  RL_TC_DUAL=0 switches it off (A/B).
-    static const int dual_env = []() { const char* e = getenv("RL_TC_DUAL"); return e ? atoi(e) : 1; }();
+    // need no per-row scaling in the loader.  Validated (the whole -m gpu suite passes with it) but measured
+    // SLOWER on B200 than the single-tile kernel, same box, back to back: 61 GB fp32 shard 14.1 vs 12.4 ms,
+    // fp16 shard 8.95 vs 8.81 ms, configs[2] 30.2 vs 21.6 ms -- with both accumulators live the epilogue no
+    // longer overlaps the next tile's MMAs and only three smem stages fit, which costs more than the halved
+    // query stream saves.  Opt-in: RL_TC_DUAL=1.
+    static const int dual_env = []() { const char* e = getenv("RL_TC_DUAL"); return e ? atoi(e) : 0; }();
     const bool dual = dual_env == 1 && !pair && t.n_groups == 1 && a_in.n_mode_blocks >= 2 &&
                       (p->metric != RL_METRIC_COSINE || p->rows_unit_scale == 1);
     if (dual) {
