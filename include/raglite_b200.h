@@ -131,8 +131,8 @@ typedef struct rl_scan_params {
   int32_t e_dtype;       /* storage of E: 0 = float32, 1 = float16 (E then points to IEEE binary16; needs
                             RL_ALGO_TCGEN05, d % 8 == 0 and rows that need no per-row scaling) */
   int32_t rows_unit_scale; /* 1: the caller guarantees (from the rl_row_stats statistics: max 1/|e| <= 2, max |e_ij| <= 1024,
-                            no all-zero row -- true for normalised embeddings) that rows can enter the fp16 scan unscaled;
-                            lets the cosine scan use the two-tiles-per-query-slice kernel.  0: unknown (always valid) */
+                            no all-zero row -- true for normalised embeddings) that rows can enter the fp16 scan unscaled,
+                            which lets the cosine scan use the two-tiles-per-query-slice kernel.  0: unknown (always valid) */
   const uint8_t* row_alive; /* optional uint8[n_rows] (NULL = all): rows that exist at all -- the tombstone mask without
                             the metadata filter (only read with RL_FLAG_COUNT_UNFILTERED) */
 } rl_scan_params;
@@ -210,6 +210,30 @@ int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, const int32_t*
 size_t rl_hits_packed_bytes(int B, int H, int with_status);
 int rl_topk_merge_packed(const void* packed, int64_t rank_stride_bytes, int R, int B, int H, int num_hits, int k,
                          float* out_sim, int64_t* out_chunk, int32_t* out_count, void* stream);
+
+/* ---- Fusion and span collation on device chunk indices: _search.py:233-280, 323-360 ------------------------
+ * rl_rrf_fuse: Reciprocal Rank Fusion of R rankings per query.  ids[B, R, L] int64 chunk indices (-1 padded at
+ * the tail of a ranking), weights[R] float64 (device), k the RRF constant (60 in the reference).
+ * score(c) = sum_r weights[r] / (k + position of c in ranking r), float64 summed ranking by ranking exactly as the
+ * reference's dict does; output ordered by descending score, ties in first-appearance order (ranking 0 first) --
+ * Python's stable sort.  out_ids[B, K] (-1 padded), out_score[B, K] float64, out_count[B].  R * L <= 4096. */
+int rl_rrf_fuse(const int64_t* ids, const double* weights, int B, int R, int L, double k, int K, int64_t* out_ids,
+                double* out_score, int32_t* out_count, void* stream);
+
+/* rl_span_collate: the ranking half of retrieve_chunk_spans (_search.py:323-360) for B lists of M retrieved chunk
+ * indices (ranked[B, M], -1 padded).  Index tables (device): chunk_doc[c] = ordinal of the chunk's document in
+ * ascending document_id order, chunk_pos[c] = Chunk.index, chunk_alive[c] (or NULL), and the lookup
+ * (doc << 32 | pos) -> chunk as two arrays sorted by key.  Every retrieved chunk is joined by its neighbours at
+ * the given position offsets inside its document (neighbors[n_neighbors], e.g. {-1, +1}), duplicates are dropped,
+ * members are ordered by (document, position) and cut into runs of consecutive positions; a run's score is the
+ * sum of 1 / (rank + 1) over its retrieved members (float64), runs are ordered by descending score (stable).
+ * Outputs, cap = M * (1 + n_neighbors) per query: out_member[B, cap] chunk indices in document order (-1 padded),
+ * out_span_start / out_span_len[B, cap] (offsets into the member row, in final span order), out_span_score[B, cap],
+ * out_n_span[B], out_n_member[B].  cap <= 4096. */
+int rl_span_collate(const int64_t* ranked, int B, int M, const int32_t* chunk_doc, const int32_t* chunk_pos,
+                    const uint8_t* chunk_alive, const uint64_t* sorted_key, const int64_t* sorted_chunk, int64_t n_chunks,
+                    const int32_t* neighbors, int n_neighbors, int64_t* out_member, int32_t* out_span_start,
+                    int32_t* out_span_len, double* out_span_score, int32_t* out_n_span, int32_t* out_n_member, void* stream);
 
 /* ---- Late-chunking pool: _embed.py:129-140 (and the simple pool :154-164) ---------------------
  * X[T,d] token embeddings (float32, row stride ld); sentence s averages rows

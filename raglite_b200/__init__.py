@@ -8,12 +8,17 @@ Drop-in surface (reference ``raglite/__init__.py`` names for this path): ``RAGLi
 from ._config import RAGLiteConfig
 from ._embed import embed_strings, register_token_embedder
 from ._index import Chunk, CorpusIndex, get_index, merge_hits, register_index, unregister_index
-from ._query_adapter import reciprocal_rank_fusion, update_query_adapter
+from ._query_adapter import update_query_adapter
 from ._search import (
     ChunkSpan,
+    collate_spans_device,
+    hybrid_search,
+    reciprocal_rank_fusion,
+    register_keyword_search,
     rerank_chunks,
     retrieve_chunk_spans,
     retrieve_chunks,
+    rrf_fuse_device,
     search_and_rerank_chunk_spans,
     search_and_rerank_chunks,
     vector_search,
@@ -25,6 +30,10 @@ __all__ = [
     "ChunkSpan",
     "CorpusIndex",
     "RAGLiteConfig",
+    "collate_spans_device",
+    "hybrid_search",
+    "register_keyword_search",
+    "rrf_fuse_device",
     "embed_strings",
     "get_index",
     "merge_hits",

@@ -557,6 +557,31 @@ class CorpusIndex:
     def _invalidate_filters(self) -> None:
         self._filter_cache.clear()
         self._n_live_rows = None
+        self._span_tables = None
+
+    def span_tables(self) -> dict[str, torch.Tensor]:
+        """Device tables ``rl_span_collate`` needs (built once per index change from the ``Chunk`` records):
+        ``chunk_doc`` = ordinal of each chunk's document in ascending ``document_id`` order (the order
+        ``retrieve_chunk_spans`` sorts by, ``_search.py:343``), ``chunk_pos`` = ``Chunk.index``, ``chunk_alive``, and the
+        lookup ``(doc << 32 | pos) -> chunk`` sorted by key."""
+        if self.chunks is None:
+            raise ValueError("The registered index holds no Chunk records (document ids / positions unknown)")
+        with self._lock:
+            if getattr(self, "_span_tables", None) is None:
+                docs = sorted({c.document_id for c in self.chunks})
+                ordinal = {d: i for i, d in enumerate(docs)}
+                doc = np.fromiter((ordinal[c.document_id] for c in self.chunks), dtype=np.int32, count=len(self.chunks))
+                pos = np.fromiter((c.index for c in self.chunks), dtype=np.int32, count=len(self.chunks))
+                key = (doc.astype(np.uint64) << np.uint64(32)) | pos.astype(np.uint32).astype(np.uint64)
+                live = np.nonzero(self._chunk_alive)[0]
+                order = live[np.argsort(key[live], kind="stable")]
+                dev = self.device
+                self._span_tables = {
+                    "chunk_doc": torch.from_numpy(doc).to(dev), "chunk_pos": torch.from_numpy(pos).to(dev),
+                    "chunk_alive": torch.from_numpy(self._chunk_alive.astype(np.uint8)).to(dev),
+                    "sorted_key": torch.from_numpy(key[order].view(np.int64)).to(dev),
+                    "sorted_chunk": torch.from_numpy(order.astype(np.int64)).to(dev)}
+            return self._span_tables
 
     @property
     def n_live_rows(self) -> int:

@@ -111,17 +111,3 @@ def update_query_adapter(  # noqa: PLR0913
         A_star = U @ VT
     local.set_query_adapter(A_star)
     return A_star
-
-
-def reciprocal_rank_fusion(rankings: Sequence[Sequence[str]], *, k: int = 60, weights: Sequence[float] | None = None
-                           ) -> tuple[list[str], list[float]]:
-    """Reciprocal Rank Fusion (``_search.py:233-254``): ``score(c) = sum_r w_r / (k + rank_r(c))``."""
-    weights = [1.0] * len(rankings) if weights is None else list(weights)
-    if len(weights) != len(rankings):
-        raise ValueError("The number of weights must match the number of rankings.")
-    score: dict[str, float] = {}
-    for ranking, w in zip(rankings, weights, strict=True):
-        for pos, cid in enumerate(ranking):
-            score[cid] = score.get(cid, 0.0) + w / (k + pos)
-    order = sorted(score.items(), key=lambda kv: kv[1], reverse=True)
-    return [c for c, _ in order], [s for _, s in order]

@@ -208,7 +208,142 @@ class ChunkSpan:
         return self.content
 
 
+# ---- fusion and span collation batched on device chunk indices -----------------------------------------------
+_KEYWORD_SEARCH: dict[str, Any] = {}
+
+
+def register_keyword_search(config_or_url: Any, fn: Any) -> None:
+    """Provide the BM25 keyword search for a database (the reference runs it as SQL full-text search inside
+    DuckDB / PostgreSQL, ``_search.py:156-230`` -- storage-engine territory, out of scope here): any callable with
+    ``keyword_search``'s signature ``(query, *, num_results, metadata_filter, config) -> (chunk_ids, scores)``."""
+    _KEYWORD_SEARCH[str(getattr(config_or_url, "db_url", config_or_url))] = fn
+
+
+def rrf_fuse_device(rankings: torch.Tensor, weights: Sequence[float], *, k: float = 60.0, num_results: int | None = None
+                    ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``rl_rrf_fuse``: Reciprocal Rank Fusion (``_search.py:233-254``) of ``rankings`` -- int64 ``[B, R, L]`` chunk
+    indices on the device, ``-1`` padded -- for a whole batch in one launch.  Returns device tensors
+    ``(ids [B, K], score float64 [B, K], count [B])``, best first, ties in first-appearance order."""
+    from . import _lib
+
+    if rankings.dtype != torch.int64 or rankings.ndim != 3 or not rankings.is_cuda:
+        raise ValueError("rankings must be a CUDA int64 [B, R, L] tensor")
+    B, R, L = (int(x) for x in rankings.shape)
+    if len(weights) != R:
+        raise ValueError("The number of weights must match the number of rankings.")
+    K = int(num_results) if num_results is not None else R * L
+    dev = rankings.device
+    w = torch.tensor(list(weights), dtype=torch.float64, device=dev)
+    out_ids = torch.empty((B, K), dtype=torch.int64, device=dev)
+    out_score = torch.empty((B, K), dtype=torch.float64, device=dev)
+    out_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rl_rrf_fuse(rankings.contiguous().data_ptr(), w.data_ptr(), B, R, L, float(k), K, out_ids.data_ptr(),
+                                   out_score.data_ptr(), out_count.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "rl_rrf_fuse")
+    return out_ids, out_score, out_count
+
+
+def reciprocal_rank_fusion(rankings: Sequence[Sequence[ChunkId]], *, k: int = 60, weights: Sequence[float] | None = None
+                           ) -> tuple[list[ChunkId], list[float]]:
+    """Drop-in ``reciprocal_rank_fusion`` (``_search.py:233-254``): the ids are interned to integers, fused by
+    ``rl_rrf_fuse`` on the device (float64, the reference's summation order) and mapped back."""
+    weights = [1.0] * len(rankings) if weights is None else list(weights)
+    if len(weights) != len(rankings):
+        raise ValueError("The number of weights must match the number of rankings.")
+    L = max((len(r) for r in rankings), default=0)
+    if L == 0:
+        return [], []
+    intern: dict[ChunkId, int] = {}
+    names: list[ChunkId] = []
+    table = np.full((1, len(rankings), L), -1, dtype=np.int64)
+    for r, ranking in enumerate(rankings):
+        for i, cid in enumerate(ranking):
+            j = intern.get(cid)
+            if j is None:
+                j = intern[cid] = len(names)
+                names.append(cid)
+            table[0, r, i] = j
+    ids, score, count = rrf_fuse_device(torch.from_numpy(table).cuda(), weights, k=float(k))
+    n = int(count[0])
+    return [names[int(j)] for j in ids[0, :n].tolist()], [float(x) for x in score[0, :n].tolist()]
+
+
+def hybrid_search(  # noqa: PLR0913
+    query: str, *, num_results: int = 3, oversample: int = 2, vector_search_weight: float = 0.75,
+    keyword_search_weight: float = 0.25, metadata_filter: MetadataFilter | None = None, config: RAGLiteConfig | None = None,
+) -> tuple[list[ChunkId], list[float]]:
+    """Drop-in ``hybrid_search`` (``_search.py:257-280``): vector search on the device index, the registered keyword
+    search (``register_keyword_search``), Reciprocal Rank Fusion of the two rankings on the device."""
+    config = config or RAGLiteConfig()
+    keyword_search = _KEYWORD_SEARCH.get(str(config.db_url))
+    if keyword_search is None:
+        raise ValueError("hybrid_search needs a keyword search for this database: raglite_b200.register_keyword_search")
+    vs_ids, _ = vector_search(query, num_results=oversample * num_results, metadata_filter=metadata_filter, config=config)
+    ks_ids, _ = keyword_search(query, num_results=oversample * num_results, metadata_filter=metadata_filter, config=config)
+    ids, score = reciprocal_rank_fusion([vs_ids, list(ks_ids)], weights=[vector_search_weight, keyword_search_weight])
+    return ids[:num_results], score[:num_results]
+
+
+def collate_spans_device(index: Any, ranked: torch.Tensor, *, neighbors: tuple[int, ...] | None = (-1, 1)
+                         ) -> dict[str, torch.Tensor]:
+    """``rl_span_collate`` for a batch of ranked chunk-index lists (int64 ``[B, M]`` on the device, ``-1`` padded,
+    LOCAL chunk indices of the index): the neighbour join, dedup, run cutting and span ranking of
+    ``retrieve_chunk_spans`` (``_search.py:323-360``) in one launch.  Returns device tensors ``member [B, cap]``,
+    ``span_start`` / ``span_len`` / ``span_score [B, cap]``, ``n_span [B]``, ``n_member [B]``."""
+    from . import _lib
+
+    local: CorpusIndex = getattr(index, "local", index)
+    tabs = local.span_tables()
+    B, M = (int(x) for x in ranked.shape)
+    nb = torch.tensor(list(neighbors or ()), dtype=torch.int32, device=local.device)
+    cap = M * (1 + int(nb.numel()))
+    dev = local.device
+    out = {"member": torch.empty((B, cap), dtype=torch.int64, device=dev),
+           "span_start": torch.empty((B, cap), dtype=torch.int32, device=dev),
+           "span_len": torch.empty((B, cap), dtype=torch.int32, device=dev),
+           "span_score": torch.empty((B, cap), dtype=torch.float64, device=dev),
+           "n_span": torch.empty((B,), dtype=torch.int32, device=dev), "n_member": torch.empty((B,), dtype=torch.int32, device=dev)}
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.rl_span_collate(
+            ranked.contiguous().data_ptr(), B, M, tabs["chunk_doc"].data_ptr(), tabs["chunk_pos"].data_ptr(),
+            tabs["chunk_alive"].data_ptr(), tabs["sorted_key"].data_ptr(), tabs["sorted_chunk"].data_ptr(),
+            int(tabs["sorted_chunk"].numel()), nb.data_ptr() if nb.numel() else None, int(nb.numel()), out["member"].data_ptr(),
+            out["span_start"].data_ptr(), out["span_len"].data_ptr(), out["span_score"].data_ptr(), out["n_span"].data_ptr(),
+            out["n_member"].data_ptr(), torch.cuda.current_stream().cuda_stream), "rl_span_collate")
+    return out
+
+
 def retrieve_chunk_spans(
+    chunk_ids: list[ChunkId] | list[Chunk], *, neighbors: tuple[int, ...] | None = (-1, 1),
+    config: RAGLiteConfig | None = None,
+) -> list[ChunkSpan]:
+    """Group chunks (plus their ``neighbors`` in the same document) into contiguous spans, ordered by the summed
+    reciprocal rank ``1 / (i + 1)`` of the chunks they contain (``_search.py:302-361``).  With a registered index
+    that holds the ``Chunk`` records the whole collation runs in ``rl_span_collate`` on chunk indices; the
+    host only maps ids to indices and indices back to records."""
+    if not chunk_ids:
+        return []
+    config = config or RAGLiteConfig()
+    index = get_index(config)
+    local = getattr(index, "local", index) if index is not None else None
+    if local is not None and local.chunks is not None and local.chunk_ids is not None:
+        ids = [c if isinstance(c, ChunkId) else c.id for c in chunk_ids]
+        pos = local._positions()
+        idx = [pos[c] for c in ids if c in pos and local._chunk_alive[pos[c]]]
+        if len(idx) == len(ids):
+            ranked = torch.tensor([idx], dtype=torch.int64, device=local.device)
+            out = collate_spans_device(local, ranked, neighbors=neighbors)
+            n_span = int(out["n_span"][0])
+            member = out["member"][0].tolist()
+            start, length = out["span_start"][0, :n_span].tolist(), out["span_len"][0, :n_span].tolist()
+            return [ChunkSpan([local.chunks[member[s + j]] for j in range(n)]) for s, n in zip(start, length, strict=True)]
+    return _retrieve_chunk_spans_host(chunk_ids, neighbors=neighbors, config=config)
+
+
+def _retrieve_chunk_spans_host(
     chunk_ids: list[ChunkId] | list[Chunk], *, neighbors: tuple[int, ...] | None = (-1, 1),
     config: RAGLiteConfig | None = None,
 ) -> list[ChunkSpan]:

@@ -144,14 +144,12 @@ def test_golden_meta_is_readable(golden_dir):
     assert len(meta["sentences"]) == z["late_chunking"].shape[0]
 
 
-def test_reciprocal_rank_fusion_matches_definition():
+def test_reciprocal_rank_fusion_argument_handling():
+    """(The fusion itself runs on the device: tests/test_fusion.py.)"""
     from raglite_b200 import reciprocal_rank_fusion
 
-    ids, scores = reciprocal_rank_fusion([["a", "b", "c"], ["b", "d"]], k=60, weights=[1.0, 2.0])
-    want = {"a": 1 / 60, "b": 1 / 61 + 2 / 60, "c": 1 / 62, "d": 2 / 61}
-    assert ids == sorted(want, key=lambda c: -want[c])
-    assert np.allclose(scores, [want[c] for c in ids])
     assert reciprocal_rank_fusion([]) == ([], [])
+    assert reciprocal_rank_fusion([[], []]) == ([], [])
     with pytest.raises(ValueError):
         reciprocal_rank_fusion([["a"]], weights=[1.0, 2.0])
 

@@ -199,8 +199,37 @@ def golden_table_rows(typing_mod: types.ModuleType) -> None:
     print("table_rows", from_text.dtype, from_list.dtype, from_blob.dtype, texts[0][:48])
 
 
+def golden_rrf() -> None:
+    """``reciprocal_rank_fusion`` (``_search.py:233-254``): the reference's own function text, compiled on its own
+    (the module around it imports SQLAlchemy / sqlmodel), run on seeded rankings with ties and duplicates."""
+    import ast
+    from collections import defaultdict
+
+    src = (REF / "_search.py").read_text()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "reciprocal_rank_fusion")
+    ns: dict = {"defaultdict": defaultdict, "ChunkId": str}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), str(REF / "_search.py"), "exec"), ns)  # noqa: S102
+    rrf = ns["reciprocal_rank_fusion"]
+    rng = np.random.default_rng(21)
+    cases = []
+    for _ in range(12):
+        R, L, universe = int(rng.integers(1, 4)), int(rng.integers(1, 40)), int(rng.integers(5, 60))
+        rankings = [[int(x) for x in rng.permutation(universe)[: int(rng.integers(0, L + 1))]] for _ in range(R)]
+        weights = [float(w) for w in rng.choice([1.0, 0.75, 0.25, 0.5], size=R)]
+        k = int(rng.choice([60, 1, 10]))
+        ids, scores = rrf([[str(c) for c in r] for r in rankings], k=k, weights=weights)
+        cases.append({"rankings": rankings, "weights": weights, "k": k, "ids": [int(c) for c in ids], "scores": [float(x) for x in scores]})
+    # the hybrid_search call shape: two rankings, weights 0.75 / 0.25 (_search.py:271-275)
+    a, b = [int(x) for x in rng.permutation(50)[:20]], [int(x) for x in rng.permutation(50)[:20]]
+    ids, scores = rrf([[str(c) for c in a], [str(c) for c in b]], weights=[0.75, 0.25])
+    cases.append({"rankings": [a, b], "weights": [0.75, 0.25], "k": 60, "ids": [int(c) for c in ids], "scores": [float(x) for x in scores]})
+    np.savez_compressed(GOLDEN / "rrf.npz", cases=np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8))
+    print("rrf", len(cases), "cases")
+
+
 if __name__ == "__main__":
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    golden_rrf()
     embed_mod, qa_mod = install_reference_stubs()
     golden_pool(embed_mod)
     golden_adapter(qa_mod)
