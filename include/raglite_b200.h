@@ -211,6 +211,21 @@ size_t rl_hits_packed_bytes(int B, int H, int with_status);
 int rl_topk_merge_packed(const void* packed, int64_t rank_stride_bytes, int R, int B, int H, int num_hits, int k,
                          float* out_sim, int64_t* out_chunk, int32_t* out_count, void* stream);
 
+/* ---- Query-adapter fit: _query_adapter.py:21-38, 172-183 ---------------------------------------------------
+ * rl_best_vectors: for every eval e and retrieved chunk chunks[e, slot] (shard-local chunk index, -1 = unused), the
+ * vector of that chunk with the largest inner product with the eval's query Q[e, :] -- argmax(embedding_matrix @ q),
+ * first maximum on ties -- written to best[e, slot, :] (float32; zeros for unused slots) and its row to best_row.
+ * E: the corpus (e_dtype 0 = float32, 1 = float16), chunk_off the CSR offsets (device int64 [n_chunks + 1]). */
+int rl_best_vectors(const void* E, int e_dtype, int64_t ld, int d, const int64_t* chunk_off, const int64_t* chunks,
+                    int n_evals, int n_slots, const float* Q, float* best, int64_t* best_row, void* stream);
+/* rl_adapter_targets: _optimize_query_target for every eval at once.  kind[e, slot] = 1 for a relevant chunk's vector
+ * (P), 0 for an irrelevant one (N), anything else = unused.  T[e, :] (float64) = q + D^T mu* with
+ * D = {p_i - (1 + alpha) n_j} and mu* = argmin_{mu >= 0} |q + D^T mu|^2 (active-set NNLS in float64 on the Gram
+ * form, see csrc/adapter_fit.cu); ok[e] = 0 when the eval has no relevant or no irrelevant chunk (T = q then, the
+ * reference skips such evals), iters[e] = outer iterations.  n_slots <= 64, |P| |N| <= 1024. */
+int rl_adapter_targets(const float* best, const uint8_t* kind, int n_evals, int n_slots, int d, const float* Q, double alpha,
+                       double* T, int32_t* ok, int32_t* iters, void* stream);
+
 /* ---- Fusion and span collation on device chunk indices: _search.py:233-280, 323-360 ------------------------
  * rl_rrf_fuse: Reciprocal Rank Fusion of R rankings per query.  ids[B, R, L] int64 chunk indices (-1 padded at
  * the tail of a ranking), weights[R] float64 (device), k the RRF constant (60 in the reference).

@@ -23,7 +23,7 @@ RL_MAX_SURVIVORS = 4096   # finalize window (include/raglite_b200.h)
 
 EXPORTS = [
     "rl_version", "rl_last_error", "rl_device_info", "rl_row_stats", "rl_row_stats_f16", "rl_chunk_row_map", "rl_adapter_apply",
-    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_unfiltered_bound", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_topk_merge_packed", "rl_hits_packed_bytes", "rl_row_mask", "rl_rrf_fuse", "rl_span_collate",
+    "rl_maxsim_workspace_bytes", "rl_maxsim_topk", "rl_maxsim_count_at_least", "rl_maxsim_unfiltered_bound", "rl_maxsim_stats", "rl_maxsim_kernel_times", "rl_maxsim_release", "rl_maxsim_copy_dump", "rl_topk_merge", "rl_topk_merge_packed", "rl_hits_packed_bytes", "rl_row_mask", "rl_rrf_fuse", "rl_span_collate", "rl_best_vectors", "rl_adapter_targets",
     "rl_segment_mean_pool", "rl_xenc_linear_image_bytes", "rl_xenc_pack_linear", "rl_xenc_linear",
     "rl_xenc_workspace_bytes", "rl_xenc_score",
 ]
@@ -92,6 +92,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.rl_hits_packed_bytes.argtypes = [i32, i32, i32]
     lib.rl_hits_packed_bytes.restype = C.c_size_t
     lib.rl_topk_merge_packed.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.rl_best_vectors.argtypes = [vp, i32, i64, i32, vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.rl_adapter_targets.argtypes = [vp, vp, i32, i32, i32, vp, C.c_double, vp, vp, vp, vp]
     lib.rl_rrf_fuse.argtypes = [vp, vp, i32, i32, i32, C.c_double, i32, vp, vp, vp, vp]
     lib.rl_span_collate.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.rl_segment_mean_pool.argtypes = [vp, i64, i32, vp, vp, i32, i32, vp, vp]

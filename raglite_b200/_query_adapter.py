@@ -5,9 +5,13 @@ via ``CorpusIndex.apply_adapter``.  The fit follows ``raglite/_query_adapter.py:
 eval, embed the question, retrieve the top chunks *without* the adapter, take each chunk's best
 vector for the query (MaxSim ``argmax(E_c @ q)``, ``:172-183``) as a positive or negative, solve the
 bounded least squares for the target ``t`` (``:21-38``), then ``M = T^T Q / n`` (+ null-space
-completion) and the orthogonal Procrustes / Frobenius-scaled solution (``:193-205``).  Retrieval and
-the per-chunk MaxSim run on the GPU index; the small dense algebra (NNLS, SVD) stays in SciPy/NumPy
-float64 exactly as in the reference.
+completion) and the orthogonal Procrustes / Frobenius-scaled solution (``:193-205``).
+
+On a single-GPU index the whole fit runs on the device, batched over the evals: retrieval through the scan
+(``vector_search_batch``), the MaxSim picks in ``rl_best_vectors``, every eval's bounded least squares in ONE
+launch of ``rl_adapter_targets`` (active-set NNLS in float64, ``csrc/adapter_fit.cu``), and the final d x d algebra
+(normalisation, ``T^T Q``, rank test, null-space completion, SVD) as float64 ``torch.linalg`` calls on the GPU.
+A sharded corpus keeps the picks per shard (summed over ranks) and solves with SciPy as the reference does.
 """
 
 from __future__ import annotations
@@ -55,6 +59,59 @@ def _best_vectors(index: Any, chunks: Sequence[int], q: np.ndarray) -> np.ndarra
     return index.sum_over_shards(out).cpu().numpy()
 
 
+def _fit_on_device(local: CorpusIndex, evals: Sequence[tuple[np.ndarray, Sequence[int]]], Qm: np.ndarray, ids: np.ndarray,
+                   counts: np.ndarray, alpha: float, metric: str) -> np.ndarray:
+    """The fit for a device-resident shard (``_query_adapter.py:160-205``), batched over the evals."""
+    from . import _lib
+
+    lib = _lib.load()
+    dev = local.device
+    n, top_k = ids.shape
+    kind = np.full((n, top_k), 2, dtype=np.uint8)     # 1 relevant, 0 irrelevant, 2 unused
+    for e, (_, relevant) in enumerate(evals):
+        rel = {int(r) for r in relevant}
+        for j in range(int(counts[e])):
+            kind[e, j] = 1 if int(ids[e, j]) in rel else 0
+    chunks = np.where(np.arange(top_k)[None, :] < counts[:, None], ids - local.chunk_base, -1).astype(np.int64)
+    with local._lock, torch.cuda.device(dev):
+        Qd = torch.from_numpy(np.ascontiguousarray(Qm, dtype=np.float32)).to(dev)
+        off = torch.from_numpy(local.chunk_off).to(dev)
+        ch = torch.from_numpy(chunks).to(dev)
+        kd = torch.from_numpy(kind).to(dev)
+        best = torch.empty((n, top_k, local.d), dtype=torch.float32, device=dev)
+        best_row = torch.empty((n, top_k), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.rl_best_vectors(local.E.data_ptr(), 1 if local.storage == "fp16" else 0, local.d, local.d, off.data_ptr(),
+                                       ch.data_ptr(), n, top_k, Qd.data_ptr(), best.data_ptr(), best_row.data_ptr(), stream),
+                   "rl_best_vectors")
+        T = torch.empty((n, local.d), dtype=torch.float64, device=dev)
+        ok = torch.empty((n,), dtype=torch.int32, device=dev)
+        iters = torch.empty((n,), dtype=torch.int32, device=dev)
+        _lib.check(lib.rl_adapter_targets(best.data_ptr(), kd.data_ptr(), n, top_k, local.d, Qd.data_ptr(), float(alpha), T.data_ptr(),
+                                          ok.data_ptr(), iters.data_ptr(), stream), "rl_adapter_targets")
+        keep = ok == 1
+        if not bool(keep.any()):
+            raise ValueError("No eval had both relevant and irrelevant chunks among the retrieved ones.")
+        # the reference casts every target back to its query's dtype (q_star.astype(q_dtype), :37) before stacking
+        half = torch.tensor([np.ravel(q).dtype == np.float16 for q, _ in evals], device=dev)
+        T = torch.where(half[:, None], T.to(torch.float16).to(torch.float64), T.to(torch.float32).to(torch.float64))
+        Q64 = torch.from_numpy(np.ascontiguousarray(Qm)).to(dev).to(torch.float64)[keep]
+        T64 = T[keep]
+        Q64 = Q64 / torch.linalg.norm(Q64, dim=1, keepdim=True)
+        if metric == "cosine":
+            T64 = T64 / torch.linalg.norm(T64, dim=1, keepdim=True)
+        m, d = Q64.shape
+        M = (1 / m) * T64.T @ Q64
+        if m < d or int(torch.linalg.matrix_rank(Q64)) < d:
+            M = M + torch.eye(d, dtype=torch.float64, device=dev) - Q64.T @ torch.linalg.pinv(Q64 @ Q64.T) @ Q64
+        if metric == "dot":
+            A = M / torch.linalg.norm(M, ord="fro") * np.sqrt(d)
+        else:
+            U, _, VT = torch.linalg.svd(M, full_matrices=False)
+            A = U @ VT
+        return A.cpu().numpy()
+
+
 def update_query_adapter(  # noqa: PLR0913
     evals: Sequence[tuple[np.ndarray, Sequence[int]]],
     *,
@@ -83,6 +140,10 @@ def update_query_adapter(  # noqa: PLR0913
     evals = list(evals)[:max_evals]
     Qm = np.stack([np.ravel(q) for q, _ in evals])
     ids, _, counts = vector_search_batch(Qm, num_results=optimize_top_k, config=cfg_no_adapter, index=index)
+    if not hasattr(index, "group") and optimize_top_k <= 64:
+        A_star = _fit_on_device(local, evals, Qm, ids, counts, optimize_gap, metric)
+        local.set_query_adapter(A_star)
+        return A_star
     Qs, Ts = [], []
     for e, (q, relevant) in enumerate(evals):
         retrieved = [int(c) for c in ids[e, : counts[e]]]

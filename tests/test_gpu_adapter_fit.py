@@ -1,0 +1,115 @@
+"""the query-adapter fit on the device -- MaxSim picks (``rl_best_vectors``) and the batched bounded
+least squares (``rl_adapter_targets``) against the oracle's ``optimize_query_target`` (pinned to the reference's own
+``_optimize_query_target`` through ``tests/golden/adapter_target.npz``) and SciPy's ``lsq_linear``."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import adapter as oad
+
+pytestmark = pytest.mark.gpu
+
+
+def _targets(best, kind, Q, alpha):
+    import torch
+
+    from raglite_b200 import _lib
+
+    lib = _lib.load()
+    n, slots, d = best.shape
+    b = torch.from_numpy(np.ascontiguousarray(best, np.float32)).cuda()
+    k = torch.from_numpy(np.ascontiguousarray(kind, np.uint8)).cuda()
+    q = torch.from_numpy(np.ascontiguousarray(Q, np.float32)).cuda()
+    T = torch.empty((n, d), dtype=torch.float64, device="cuda")
+    ok = torch.empty(n, dtype=torch.int32, device="cuda")
+    it = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.check(lib.rl_adapter_targets(b.data_ptr(), k.data_ptr(), n, slots, d, q.data_ptr(), float(alpha), T.data_ptr(), ok.data_ptr(),
+                                      it.data_ptr(), torch.cuda.current_stream().cuda_stream), "rl_adapter_targets")
+    return T.cpu().numpy(), ok.cpu().numpy(), it.cpu().numpy()
+
+
+def test_adapter_targets_match_the_reference_golden(golden_dir):
+    z = np.load(golden_dir / "adapter_target.npz")
+    for i in range(3):
+        q, P, N, t = z[f"q{i}"], z[f"P{i}"], z[f"N{i}"], z[f"t{i}"]
+        best = np.concatenate([P, N]).astype(np.float32)[None]
+        kind = np.array([[1] * len(P) + [0] * len(N)], np.uint8)
+        T, ok, _ = _targets(best, kind, q.astype(np.float32)[None], 0.05)
+        assert ok[0] == 1
+        got = T[0].astype(q.dtype)                      # the reference casts back to the query dtype (:37)
+        ulp = np.abs(got.view(np.int16 if q.dtype == np.float16 else np.int32).astype(np.int64) -
+                     t.view(np.int16 if q.dtype == np.float16 else np.int32).astype(np.int64))
+        assert ulp.max() <= 1 and (ulp > 0).mean() < 0.02, (i, ulp.max())
+        assert np.allclose(T[0], oad.optimize_query_target(q.astype(np.float64), P, N, alpha=0.05), atol=1e-9)
+
+
+def test_adapter_targets_batched_against_scipy():
+    rng = np.random.default_rng(0)
+    d, slots, n = 256, 40, 24
+    best = rng.standard_normal((n, slots, d)).astype(np.float32)
+    best /= np.linalg.norm(best, axis=2, keepdims=True)
+    Q = rng.standard_normal((n, d)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    best[:, :, :] = 0.6 * best + 0.4 * Q[:, None, :]                 # retrieved vectors resemble the query
+    kind = np.full((n, slots), 2, np.uint8)
+    for e in range(n):
+        used = int(rng.integers(2, slots + 1))
+        kind[e, :used] = (rng.random(used) < 0.3).astype(np.uint8)
+    kind[0, :] = 0            # no relevant chunk: skipped
+    kind[1, :5] = 1; kind[1, 5:] = 2   # no irrelevant chunk: skipped
+    kind[2, :20] = 1; kind[2, 20:40] = 0   # 20 x 20 = 400 generators
+    best[3, 1] = best[3, 0]    # duplicated example vectors (dependent generators)
+    T, ok, iters = _targets(best, kind, Q, 0.05)
+    assert ok[0] == 0 and ok[1] == 0 and np.array_equal(T[0], Q[0].astype(np.float64))
+    worst = 0.0
+    for e in range(2, n):
+        P, N = best[e][kind[e] == 1], best[e][kind[e] == 0]
+        if len(P) == 0 or len(N) == 0:
+            assert ok[e] == 0
+            continue
+        assert ok[e] == 1 and iters[e] < 6 * len(P) * len(N) + 64
+        want = oad.optimize_query_target(Q[e].astype(np.float64), P, N, alpha=0.05)
+        worst = max(worst, float(np.abs(T[e] - want).max()))
+    assert worst < 1e-8, worst
+
+
+def test_best_vectors_pick_the_maxsim_row():
+    import torch
+    from synth import make_corpus, make_queries
+
+    import raglite_b200 as rl
+    from raglite_b200 import _lib
+
+    lib = _lib.load()
+    for storage in ("fp32", "fp16"):
+        E, off = make_corpus(300, (1, 9), 64, seed=7, fp16_round=True)
+        idx = rl.CorpusIndex(E, off, storage=storage)
+        Q = make_queries(E, 6, seed=8)
+        rng = np.random.default_rng(9)
+        chunks = rng.integers(0, len(off) - 1, size=(6, 10)).astype(np.int64)
+        chunks[2, 7:] = -1
+        ch = torch.from_numpy(chunks).cuda()
+        Qd = torch.from_numpy(Q).cuda()
+        offd = torch.from_numpy(off).cuda()
+        best = torch.empty((6, 10, 64), dtype=torch.float32, device="cuda")
+        rows = torch.empty((6, 10), dtype=torch.int64, device="cuda")
+        _lib.check(lib.rl_best_vectors(idx.E.data_ptr(), 1 if storage == "fp16" else 0, 64, 64, offd.data_ptr(), ch.data_ptr(), 6, 10,
+                                       Qd.data_ptr(), best.data_ptr(), rows.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "rl_best_vectors")
+        best, rows = best.cpu().numpy(), rows.cpu().numpy()
+        for e in range(6):
+            for j in range(10):
+                c = chunks[e, j]
+                if c < 0:
+                    assert rows[e, j] == -1 and not best[e, j].any()
+                    continue
+                Ec = E[off[c]:off[c + 1]]
+                want = int(off[c]) + oad.maxsim_row(Ec, Q[e])          # argmax(embedding_matrix @ q), _query_adapter.py:172-183
+                s = Ec.astype(np.float64) @ Q[e].astype(np.float64)
+                if np.sort(s)[-1] - (np.sort(s)[-2] if len(s) > 1 else -np.inf) > 1e-6:
+                    assert rows[e, j] == want
+                assert np.array_equal(best[e, j], E[rows[e, j]])
