@@ -620,6 +620,20 @@ class CorpusIndex:
             self._ws[key] = ws
         return ws
 
+    def close(self) -> None:
+        """Release the per-stream workspaces (and the timing events the library keeps per workspace pointer)."""
+        with self._lock:
+            for ws in self._ws.values():
+                self.lib.rl_maxsim_release(_ptr(ws))
+            self._ws.clear()
+            self.last_ws = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001, S110  (interpreter shutdown: the library may be gone)
+            pass
+
     def scan(  # noqa: PLR0913
         self, Q: torch.Tensor, *, k: int, num_hits: int, metric: str = "cosine", algo: str = "auto",
         row_allowed: torch.Tensor | None = None, flags: int = 0, sample_stride: int = 0, cand_cap: int = 0,

@@ -841,6 +841,155 @@ __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restr
   }
 }
 
+// Two 16-query tiles per warp and key block: the K / V fragments are fetched from shared memory once and feed both
+// tiles' MMAs, and the two tiles' softmax chains (max -> ex2 -> sum -> pack) interleave.  ncu on the one-tile
+// kernel showed no saturated pipe (ex2 32 %, HMMA 30 %, issue 37 %) with three CTAs = 12 warps per SM: the
+// dependent chain of a single tile per warp, not a throughput limit, set the pace.
+__global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
+                                                         int H, int n_heads, float scale_log2e, __half* __restrict__ ctx) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  const int seq = blockIdx.x, head = blockIdx.y;
+  const int t0 = cu[seq], L = cu[seq + 1] - t0;
+  const int Lp = (L + 63) / 64 * 64;
+  __half* Ks = reinterpret_cast<__half*>(att_smem);
+  __half* Vs = Ks + (size_t)Lp * kAttPitch;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t ld = (size_t)3 * H;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
+    const int j = idx >> 2, c = idx & 3;
+    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+    if (j < L) {
+      const __half* base = qkv + (size_t)(t0 + j) * ld + head * 32 + c * 8;
+      kv = __ldg(reinterpret_cast<const uint4*>(base + H));
+      vv = __ldg(reinterpret_cast<const uint4*>(base + 2 * H));
+    }
+    *reinterpret_cast<uint4*>(Ks + (size_t)j * kAttPitch + c * 8) = kv;
+    *reinterpret_cast<uint4*>(Vs + (size_t)j * kAttPitch + c * 8) = vv;
+  }
+  __syncthreads();
+  const int r = lane >> 2, cp = (lane & 3) * 2;
+  auto load_q = [&](int qb, uint32_t (&a)[2][4]) {   // A fragments of S = Q K^T for one 16-query tile (rows >= L read as zero)
+    const int q0 = qb * 16 + r, q1 = q0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* p0 = qkv + (size_t)(t0 + q0) * ld + head * 32 + ks * 16 + cp;
+      const __half* p1 = qkv + (size_t)(t0 + q1) * ld + head * 32 + ks * 16 + cp;
+      a[ks][0] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0)) : 0u;
+      a[ks][1] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1)) : 0u;
+      a[ks][2] = q0 < L ? __ldg(reinterpret_cast<const uint32_t*>(p0 + 8)) : 0u;
+      a[ks][3] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1 + 8)) : 0u;
+    }
+  };
+  for (int pb = warp; pb * 32 < L; pb += 4) {   // this warp's pair of tiles: queries [32 pb, 32 pb + 32)
+    uint32_t a[2][2][4];
+    load_q(2 * pb, a[0]);
+    load_q(2 * pb + 1, a[1]);
+    float m[2][2], l[2][2], O[2][4][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      m[t][0] = m[t][1] = -INFINITY;
+      l[t][0] = l[t][1] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) O[t][i][e] = 0.f;
+    }
+    for (int kb = 0; kb < Lp; kb += 64) {
+      float S[2][8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t b[4];
+        ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) S[t][j][e] = 0.f;
+          mma16816(S[t][j], a[t][0], b[0], b[1]);
+          mma16816(S[t][j], a[t][1], b[2], b[3]);
+        }
+      }
+      if (kb + 64 > L) {   // only the last key block holds padding keys
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (kb + j * 8 + cp + (e & 1) >= L) S[t][j][e] = -INFINITY;
+      }
+      float mn[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mx0 = fmaxf(mx0, fmaxf(S[t][j][0], S[t][j][1]));
+          mx1 = fmaxf(mx1, fmaxf(S[t][j][2], S[t][j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        mn[t][0] = fmaxf(m[t][0], mx0 * scale_log2e);
+        mn[t][1] = fmaxf(m[t][1], mx1 * scale_log2e);
+        const float c0 = ex2_approx(m[t][0] - mn[t][0]), c1 = ex2_approx(m[t][1] - mn[t][1]);
+        l[t][0] *= c0; l[t][1] *= c1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { O[t][i][0] *= c0; O[t][i][1] *= c0; O[t][i][2] *= c1; O[t][i][3] *= c1; }
+        m[t][0] = mn[t][0]; m[t][1] = mn[t][1];
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pexp = ex2_approx(fmaf(S[t][j][e], scale_log2e, e < 2 ? -mn[t][0] : -mn[t][1]));   // -inf -> 0
+            S[t][j][e] = pexp;
+            if (e < 2) l[t][0] += pexp; else l[t][1] += pexp;
+          }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[2][4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          pa[t][0] = pack_half2(S[t][2 * kk][0], S[t][2 * kk][1]);
+          pa[t][1] = pack_half2(S[t][2 * kk][2], S[t][2 * kk][3]);
+          pa[t][2] = pack_half2(S[t][2 * kk + 1][0], S[t][2 * kk + 1][1]);
+          pa[t][3] = pack_half2(S[t][2 * kk + 1][2], S[t][2 * kk + 1][3]);
+        }
+#pragma unroll
+        for (int dn2 = 0; dn2 < 2; ++dn2) {
+          uint32_t vb[4];
+          ldsm_x4_trans(vb, Vs + (size_t)(kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kAttPitch +
+                                (dn2 * 2 + (lane >> 4)) * 8);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mma16816(O[t][dn2 * 2], pa[t], vb[0], vb[1]);
+            mma16816(O[t][dn2 * 2 + 1], pa[t], vb[2], vb[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      float l0 = l[t][0], l1 = l[t][1];
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+      const int q0 = (2 * pb + t) * 16 + r, q1 = q0 + 8;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        if (q0 < L) *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q0) * H + head * 32 + dn * 8 + cp) = pack_half2(O[t][dn][0] * inv0, O[t][dn][1] * inv0);
+        if (q1 < L) *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + q1) * H + head * 32 + dn * 8 + cp) = pack_half2(O[t][dn][2] * inv1, O[t][dn][3] * inv1);
+      }
+    }
+  }
+}
+
 // ---- pooler + classifier ----------------------------------------------------------------------------------
 // logit[s] = Wc . tanh(Wp h_s + bp) + bc with h_s the [CLS] row of sequence s.  A warp owns kClsSeqs
 // sequences (their [CLS] rows sit in shared memory as fp32) and walks the H pooler outputs; for one output
@@ -1051,13 +1200,16 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   static const bool att_quad = []() { const char* e = getenv("RL_XENC_ATT_QUAD"); return e ? atoi(e) != 0 : false; }();
   RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   RL_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  RL_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   const float scale = 1.4426950408889634f / sqrtf(32.f);  // softmax in the exp2 domain
   for (int l = 0; l < w->n_layers; ++l) {
     const rl_xenc_layer& L = w->layers[l];
     int rc = launch_linear(hidden, L.qkv_img, L.qkv_bias, qkv, T, 3 * H, H, 0, sms, stream);
     if (rc != RL_OK) return rc;
+    static const bool att2 = []() { const char* e = getenv("RL_XENC_ATT2"); return e == nullptr || atoi(e) != 0; }();
     auto attention = [&](size_t smem, int lo, int hi) {
-      if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
+      if (att2 && lo == 0 && hi == max_len) attention2_kernel<<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
+      else if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
       else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
     };
     // Measured (ncu launch list, 51 k tokens per call, mean 200): two bucketed launches 86 + 64 us vs 141 us for one
