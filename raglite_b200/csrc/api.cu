@@ -71,7 +71,7 @@ int make_layout(const rl_scan_params* p, int sm_count, Layout* L) {
   L->mode_sql = p->num_hits > 0;
   L->H = L->mode_sql ? p->num_hits : p->k;
   const int64_t sel_final = L->mode_sql ? p->num_hits : (int64_t)(p->k - 1) * p->max_vecs_per_chunk + 1;
-  RL_REQUIRE(sel_final + sel_final / 4 <= RL_MAX_SURVIVORS, RL_EUNSUPPORTED,
+  RL_REQUIRE(sel_final <= RL_MAX_SURVIVORS, RL_EUNSUPPORTED,
              "selection size %lld exceeds the %d-survivor finalize window (k=%d num_hits=%d max_vecs=%d)",
              (long long)sel_final, RL_MAX_SURVIVORS, p->k, p->num_hits, p->max_vecs_per_chunk);
   L->sel_k = L->mode_sql ? p->num_hits : p->k;  // order statistic searched in the sample
@@ -437,7 +437,7 @@ extern "C" int rl_topk_merge(const float* hit_sim, const int64_t* hit_chunk, con
   MergeArgs m;
   m.hit_sim = hit_sim; m.hit_chunk = hit_chunk; m.hit_count = hit_count; m.out_sim = out_sim;
   m.out_chunk = out_chunk; m.out_count = out_count; m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k;
-  m.win = 0; m.sim_rs = 0; m.chunk_rs = 0; m.count_rs = 0;
+  m.win = 0; m.prefilter = 0; m.sim_rs = 0; m.chunk_rs = 0; m.count_rs = 0;
   return launch_merge(m, (cudaStream_t)stream);
 }
 
@@ -461,7 +461,7 @@ extern "C" int rl_topk_merge_packed(const void* packed, int64_t rank_stride_byte
   m.hit_sim = reinterpret_cast<const float*>(base + (size_t)B * H * 8);
   m.hit_count = reinterpret_cast<const int32_t*>(base + (size_t)B * H * 12);
   m.out_sim = out_sim; m.out_chunk = out_chunk; m.out_count = out_count;
-  m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k; m.win = 0;
+  m.R = R; m.B = B; m.H = H; m.num_hits = num_hits; m.k = k; m.win = 0; m.prefilter = 0;
   m.chunk_rs = rank_stride_bytes / 8; m.sim_rs = rank_stride_bytes / 4; m.count_rs = rank_stride_bytes / 4;
   return launch_merge(m, (cudaStream_t)stream);
 }

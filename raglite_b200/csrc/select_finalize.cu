@@ -56,6 +56,49 @@ __device__ void find_bin_from_top(const uint32_t* hist, int K, int* res) {
   }
 }
 
+// Narrow n 64-bit composites -- larger = better, 0 = absent, the non-zero ones all distinct -- to the K best plus at
+// most (window - K) more, by a radix select over the composite from the top digit down (12 bits per pass; at full
+// resolution a digit holds one composite, so the loop always ends inside the window), and gather ~composite (an
+// ascending sort key) into out[0 .. *count).  All threads of the block must call it; comp_of(i) may read global memory.
+template <class Comp>
+__device__ void block_gather_top(int n, int K, int window, Comp comp_of, uint64_t* out, uint32_t* hist, int* res, int* count) {
+  uint64_t prefix = 0;      // value of the top `bits` bits of the K-th largest composite
+  int bits = 0, need = K;
+  while (bits < 64) {
+    const int w = min(12, 64 - bits);
+    const int shift = 64 - bits - w;
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t c = comp_of(i);
+      if (c != 0ull && (bits == 0 || (c >> (64 - bits)) == prefix)) atomicAdd(&hist[(uint32_t)(c >> shift) & ((1u << w) - 1u)], 1u);
+    }
+    __syncthreads();
+    find_bin_from_top(hist, need, res);
+    __syncthreads();
+    const int bin = res[0] < 0 ? 0 : res[0];     // < 0: fewer than `need` composites left -> take everything
+    const int above = res[0] < 0 ? 0 : res[1];
+    const int in_bin = (int)hist[bin];
+    const bool all = res[0] < 0;
+    __syncthreads();
+    prefix = (prefix << w) | (uint64_t)bin;
+    bits += w;
+    need -= above;
+    // composites with top bits > prefix number K - need; those == prefix number in_bin
+    if (all || (K - need) + in_bin <= window) break;
+  }
+  if (threadIdx.x == 0) *count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t c = comp_of(i);
+    if (c != 0ull && (c >> (64 - bits)) >= prefix) {
+      const int pos = atomicAdd(count, 1);
+      if (pos < window) out[pos] = ~c;
+    }
+  }
+  __syncthreads();
+}
+
 // Lower bound (24-bit bin edge, i.e. within 2^-15 relative) of the K-th largest of get(0..n).
 // -inf when fewer than K finite values exist.  All threads of the block must call it.
 template <class Get>
@@ -561,40 +604,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeArg
       const uint32_t o = __float_as_uint(c.key);
       return o == 0u ? 0ull : (((uint64_t)o << 32) | (uint32_t)(~(uint32_t)c.row));
     };
-    uint64_t prefix = 0;      // value of the top `bits` bits of the sel_k-th largest composite
-    int bits = 0, need = f.sel_k;
-    while (bits < 64) {
-      const int w = min(12, 64 - bits);
-      const int shift = 64 - bits - w;
-      for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0;
-      __syncthreads();
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t c = comp_of(i);
-        if (c != 0ull && (bits == 0 || (c >> (64 - bits)) == prefix)) atomicAdd(&hist[(uint32_t)(c >> shift) & ((1u << w) - 1u)], 1u);
-      }
-      __syncthreads();
-      find_bin_from_top(hist, need, res);
-      __syncthreads();
-      const int bin = res[0] < 0 ? 0 : res[0];     // < 0: fewer than `need` survivors left -> take everything
-      const int above = res[0] < 0 ? 0 : res[1];
-      const int in_bin = (int)hist[bin];
-      __syncthreads();
-      prefix = (prefix << w) | (uint64_t)bin;
-      bits += w;
-      need -= above;
-      // survivors with top bits > prefix number sel_k - need; those == prefix number in_bin
-      if (res[0] < 0 || (f.sel_k - need) + in_bin <= RL_MAX_SURVIVORS) break;
-    }
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint64_t c = comp_of(i);
-      if (c != 0ull && (c >> (64 - bits)) >= prefix) {
-        const int pos = atomicAdd(&s_count, 1);
-        if (pos < RL_MAX_SURVIVORS) keys[pos] = ~c;   // ~composite = (~ord(sim)) << 32 | row
-      }
-    }
-    __syncthreads();
+    block_gather_top(n, f.sel_k, RL_MAX_SURVIVORS, comp_of, keys, hist, res, &s_count);
     ns = min(s_count, RL_MAX_SURVIVORS);
   }
   int npow2 = 1;
@@ -659,16 +669,33 @@ __global__ void __launch_bounds__(kSelThreads) merge_kernel(const MergeArgs m) {
   const int64_t sim_rs = m.sim_rs ? m.sim_rs : (int64_t)m.B * m.H;
   const int64_t chunk_rs = m.chunk_rs ? m.chunk_rs : (int64_t)m.B * m.H;
   const int64_t count_rs = m.count_rs ? m.count_rs : (int64_t)m.B;
-  for (int r = 0; r < m.R; ++r) {
-    const int cnt = min(m.hit_count[(size_t)r * count_rs + b], m.H);
-    __shared__ int base;
-    if (threadIdx.x == 0) { base = s_n; s_n += cnt; }
+  if (m.prefilter) {
+    // More gathered hits than the shared-memory window (R * H > 8192: many shards x a large num_hits): only the
+    // num_hits best overall can matter, so select them straight from global memory -- a radix select over the
+    // composite (sim desc, shard-major position asc; all distinct) -- and sort just those.
+    uint32_t* hist = reinterpret_cast<uint32_t*>(flags + win);   // [kBins]
+    __shared__ int res[2];
+    auto comp_of = [&](int idx) -> uint64_t {
+      const int r = idx / m.H, i = idx % m.H;
+      if (i >= min(m.hit_count[(size_t)r * count_rs + b], m.H)) return 0ull;
+      const uint32_t o = f2ord(m.hit_sim[(size_t)r * sim_rs + (size_t)b * m.H + i]);
+      return o == 0u ? 0ull : (((uint64_t)o << 32) | (uint32_t)(~(uint32_t)idx));
+    };
+    block_gather_top(m.R * m.H, m.num_hits, win, comp_of, keys, hist, res, &s_n);
+    if (threadIdx.x == 0 && s_n > win) s_n = win;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const size_t e = (size_t)r * sim_rs + (size_t)b * m.H + i;
-      keys[base + i] = ((uint64_t)(~f2ord(m.hit_sim[e])) << 32) | (uint32_t)(r * m.H + i);
+  } else {
+    for (int r = 0; r < m.R; ++r) {
+      const int cnt = min(m.hit_count[(size_t)r * count_rs + b], m.H);
+      __shared__ int base;
+      if (threadIdx.x == 0) { base = s_n; s_n += cnt; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const size_t e = (size_t)r * sim_rs + (size_t)b * m.H + i;
+        keys[base + i] = ((uint64_t)(~f2ord(m.hit_sim[e])) << 32) | (uint32_t)(r * m.H + i);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   const int n = s_n;
   int npow2 = 1;
@@ -761,13 +788,16 @@ int launch_finalize(const FinalizeArgs& f, int B, cudaStream_t stream) {
 
 int launch_merge(const MergeArgs& m_in, cudaStream_t stream) {
   MergeArgs m = m_in;
-  RL_REQUIRE((int64_t)m.R * m.H <= kMergeMax, RL_EUNSUPPORTED, "rl_topk_merge: R*H=%lld exceeds %d",
-             (long long)m.R * m.H, kMergeMax);
+  const int64_t total = (int64_t)m.R * m.H;
+  m.prefilter = total > kMergeMax ? 1 : 0;
+  RL_REQUIRE(!m.prefilter || (m.num_hits > 0 && m.num_hits <= kMergeMax && total < (1ll << 31)), RL_EUNSUPPORTED,
+             "rl_topk_merge: R*H=%lld exceeds %d (supported beyond that only with 0 < num_hits <= %d)", (long long)total,
+             kMergeMax, kMergeMax);
   int win = 32;
-  while (win < m.R * m.H) win <<= 1;
+  while (win < (m.prefilter ? m.num_hits : total)) win <<= 1;
   m.win = win;
   // sized by the problem, not by the cap: R*H = 3200 -> 86 KB -> two CTAs per SM, a 256-query batch is one wave
-  const size_t smem = (size_t)win * (8 + 8 + 4 + 1);
+  const size_t smem = (size_t)win * (8 + 8 + 4 + 1) + (m.prefilter ? (size_t)kBins * 4 : 0);
   RL_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_kernel<<<m.B, kSelThreads, smem, stream>>>(m);
   RL_CUDA_CHECK(cudaGetLastError());

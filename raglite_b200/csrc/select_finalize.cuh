@@ -45,7 +45,8 @@ struct MergeArgs {
   int64_t* out_chunk;         // [B, k]
   int32_t* out_count;         // [B]
   int32_t R, B, H, num_hits, k;
-  int32_t win;                // set by launch_merge: power of two >= R * H
+  int32_t win;                // set by launch_merge: power of two >= R * H (or >= num_hits when prefiltering)
+  int32_t prefilter;          // set by launch_merge: R * H exceeds the window, select the num_hits best from global memory first
   int64_t sim_rs, chunk_rs, count_rs;  // element strides between the ranks' lists (0 = contiguous [R, B, H] / [R, B])
 };
 

@@ -585,3 +585,30 @@ def test_rank_then_filter_is_proven_without_a_second_pass(rl, monkeypatch):
         worst = np.sort(d[rows_ok])[79]
         assert ub[b] >= int((d[np.repeat(alive, np.diff(off))] <= worst).sum())
         check_sql_semantics(E, off, Q[b], chunk[b, :count[b]], sim[b, :count[b]], k=10, allowed_chunks=tagged & alive)
+
+
+def test_merge_of_more_hits_than_the_window(rl):
+    """R * H > 8192 gathered hits (many shards x a large num_hits): ``rl_topk_merge`` first selects the num_hits best
+    straight from global memory, then sorts / groups those -- same answer as merging everything."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    R, B, H, k = 8, 3, 2000, 500
+    sim = np.sort(rng.random((R, B, H)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    sim[:, 1, :] = np.round(sim[:, 1, :], 2)                    # massive ties in query 1
+    sim[:, 1, :] = np.sort(sim[:, 1, :], axis=1)[:, ::-1]
+    chunk = rng.integers(0, 3000, size=(R, B, H)).astype(np.int64)
+    count = rng.integers(H - 50, H + 1, size=(R, B)).astype(np.int32)
+    out_sim, out_chunk, out_count = rl.merge_hits(torch.from_numpy(sim).cuda(), torch.from_numpy(chunk).cuda(),
+                                                  torch.from_numpy(count).cuda(), num_hits=H, k=k)
+    out_sim, out_chunk, out_count = out_sim.cpu().numpy(), out_chunk.cpu().numpy(), out_count.cpu().numpy()
+    for b in range(B):
+        s = np.concatenate([sim[r, b, :count[r, b]] for r in range(R)])
+        c = np.concatenate([chunk[r, b, :count[r, b]] for r in range(R)])
+        o = np.argsort(-s.astype(np.float64), kind="stable")[:H]    # ties: shard-major position, like the kernel
+        s, c = s[o], c[o]
+        _, first = np.unique(c, return_index=True)
+        keep = np.sort(first)[:k]
+        n = int(out_count[b])
+        assert n == len(keep)
+        assert np.array_equal(out_chunk[b, :n], c[keep]) and np.array_equal(out_sim[b, :n], s[keep])
