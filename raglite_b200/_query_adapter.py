@@ -120,11 +120,18 @@ def update_query_adapter(  # noqa: PLR0913
     optimize_gap: float = 0.05,
     config: RAGLiteConfig | None = None,
     index: Any | None = None,
+    solver: str = "device",
 ) -> np.ndarray:
     """Compute the optimal query adapter and attach it to the index.
 
     ``evals`` are ``(question_embedding, relevant_chunk_indices)`` pairs -- what the reference reads from
     its ``Eval`` table and ``embed_strings`` (``_query_adapter.py:151-160``).
+
+    ``solver="device"`` (default on a single-GPU index) solves every eval's bounded least squares exactly on the
+    device (the unique projection; it satisfies the margin constraints to 1e-16).  ``solver="scipy"`` calls
+    ``scipy.optimize.lsq_linear`` per eval as the reference does: identical to the device answer to ~1e-8 on small
+    instances, but SciPy's trust-region iteration stops up to ~1e-3 short of the optimum on the larger rank-deficient
+    ones (20 x 20 positives x negatives), so choose it only to reproduce the reference's iterate.
     """
     config = config or RAGLiteConfig()
     index = index if index is not None else get_index(config)
@@ -140,7 +147,9 @@ def update_query_adapter(  # noqa: PLR0913
     evals = list(evals)[:max_evals]
     Qm = np.stack([np.ravel(q) for q, _ in evals])
     ids, _, counts = vector_search_batch(Qm, num_results=optimize_top_k, config=cfg_no_adapter, index=index)
-    if not hasattr(index, "group") and optimize_top_k <= 64:
+    if solver not in ("device", "scipy"):
+        raise ValueError("solver must be 'device' or 'scipy'")
+    if solver == "device" and not hasattr(index, "group") and optimize_top_k <= 64:
         A_star = _fit_on_device(local, evals, Qm, ids, counts, optimize_gap, metric)
         local.set_query_adapter(A_star)
         return A_star

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kFitThreads) adapter_targets_kernel(const floa
   int* widx = reinterpret_cast<int*>(rhs + kFitMaxR);        // [kFitMaxR] slot of the i-th example (positives first)
   int* S = widx + kFitMaxR;                                  // [kFitMaxR] passive set (generator indices)
   uint8_t* inS = reinterpret_cast<uint8_t*>(S + kFitMaxR);   // [kFitMaxM] 1: passive, 2: rejected until the next successful step
-  __shared__ int nP, nN, s_sz, s_pick, s_flag, s_iter;
+  __shared__ int nP, nN, s_sz, s_pick, s_flag, s_iter, s_fresh;
   __shared__ double s_best, s_step;
   const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const uint8_t* kd = kind + (size_t)e * n_slots;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kFitThreads) adapter_targets_kernel(const floa
     }
     __syncthreads();
     if (s_pick < 0 || s_sz >= r || s_iter > max_iter) break;
-    if (tid == 0) { S[s_sz] = s_pick; inS[s_pick] = 1; ++s_sz; }
+    if (tid == 0) { S[s_sz] = s_pick; inS[s_pick] = 1; ++s_sz; s_fresh = 1; }
     __syncthreads();
     // inner loop: least squares on the passive set, step back to feasibility if a coefficient went non-positive
     while (true) {
@@ -190,6 +190,11 @@ __global__ void __launch_bounds__(kFitThreads) adapter_targets_kernel(const floa
       if (tid == 0) {
         for (int a = 0; a < s; ++a) { double v = rhs[a]; for (int k = 0; k < a; ++k) v -= Hs[a * kFitMaxR + k] * z[k]; z[a] = v / Hs[a * kFitMaxR + a]; }
         for (int a = s - 1; a >= 0; --a) { double v = z[a]; for (int k = a + 1; k < s; ++k) v -= Hs[k * kFitMaxR + a] * z[k]; z[a] = v / Hs[a * kFitMaxR + a]; }
+        // Lawson-Hanson safeguard: the column just added must come out positive in the first solve (it does in exact
+        // arithmetic, its gradient was positive); if rounding says otherwise, adding it would cycle -- treat it as
+        // dependent instead.
+        if (s_fresh && z[s - 1] <= 0.0) s_flag = 2;
+        s_fresh = 0;
         double step = 1.0;
         bool feasible = true;
         for (int a = 0; a < s; ++a)
@@ -197,6 +202,11 @@ __global__ void __launch_bounds__(kFitThreads) adapter_targets_kernel(const floa
         s_step = feasible ? -1.0 : step;
       }
       __syncthreads();
+      if (s_flag == 2) {
+        if (tid == 0) { --s_sz; inS[S[s_sz]] = 2; }
+        __syncthreads();
+        break;
+      }
       if (s_step < 0.0) {
         for (int a = tid; a < s; a += blockDim.x) mu[S[a]] = z[a];
         for (int j = tid; j < m; j += blockDim.x) if (inS[j] == 2) inS[j] = 0;   // a real step: rejected columns may come back
