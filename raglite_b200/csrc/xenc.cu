@@ -130,6 +130,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
 
 __host__ __device__ inline uint32_t lin_stage_bytes() { return kABytes + kMaxN * 128u; }
 
+// MC: a cluster of two CTAs works on two token tiles of the SAME output pass; every weight slice is fetched from
+// L2 once per cluster -- CTA r issues half r with .multicast::cluster, it lands at the same offset in both CTAs --
+// so the L2 -> SM weight stream, which bounds the K = 1536 layer (FFN-down: 590 KB of weights per 128-token
+// tile, 788 MB per launch at ~8.7 TB/s), halves.  A stage is refilled only when BOTH CTAs' MMAs have released
+// it: the commit that frees a stage is multicast to both CTAs' empty barriers (count 2).
+template <bool MC>
 __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -143,14 +149,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (t.T + kTileM - 1) / kTileM;
-  const int64_t n_items = (int64_t)m_tiles * t.n_pass;  // item = m_tile * n_pass + pass
-  const int64_t first = blockIdx.x, stride = gridDim.x;
+  // item = m_unit * n_pass + pass; a unit is one token tile, or (MC) the pair of tiles 2u, 2u + 1 of a cluster
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  const int m_units = MC ? (m_tiles + 1) / 2 : m_tiles;
+  const int64_t n_items = (int64_t)m_units * t.n_pass;
+  const int64_t first = MC ? blockIdx.x >> 1 : blockIdx.x, stride = MC ? gridDim.x >> 1 : gridDim.x;
   const int64_t my_items = first < n_items ? (n_items - first + stride - 1) / stride : 0;
+  auto tile_of = [&](int64_t item) -> int { const int u = (int)(item / t.n_pass); return MC ? 2 * u + (int)crank : u; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < t.stages; ++i) {
       mbar_init(&full[i], (t.cp_async ? kNumLoaderWarps * 32 : kNumLoaderWarps) + 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MC ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -161,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
   if (warp == kMmaWarp) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // the peer's barriers are initialised before any multicast / remote commit reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       if (g >= n_slices) return;
       const int64_t it = g / t.n_ks;
       const int ks = (int)(g - it * t.n_ks);
-      const int m_tile = (int)((first + it * stride) / t.n_pass);
+      const int m_tile = tile_of(first + it * stride);
       const int col = ks * kSliceK + j * 8;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
       for (int64_t g = 0; g < n_slices; ++g) {
         const int64_t it = g / t.n_ks;
         const int ks = (int)(g - it * t.n_ks);
-        const int m_tile = (int)((first + it * stride) / t.n_pass);
+        const int m_tile = tile_of(first + it * stride);
         const int col = ks * kSliceK + j * 8;
         mbar_wait(&empty[stage], phase ^ 1u);
         const uint32_t A = smem_u32(base + (size_t)stage * sbytes);
@@ -248,7 +259,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
         for (int ks = 0; ks < t.n_ks; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full[stage], wbytes);
-          bulk_g2s(base + (size_t)stage * sbytes + kABytes, src + (size_t)ks * nb * kSliceK, wbytes, &full[stage]);
+          if (MC) {   // this CTA's half of the slice, to both CTAs of the cluster
+            const uint32_t half = wbytes / 2;
+            bulk_g2s_multicast(base + (size_t)stage * sbytes + kABytes + (size_t)crank * half,
+                               reinterpret_cast<const unsigned char*>(src + (size_t)ks * nb * kSliceK) + (size_t)crank * half, half,
+                               &full[stage], (uint16_t)3);
+          } else {
+            bulk_g2s(base + (size_t)stage * sbytes + kABytes, src + (size_t)ks * nb * kSliceK, wbytes, &full[stage]);
+          }
           if (++stage == t.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -276,7 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
 #pragma unroll
           for (int k = 0; k < kSliceK / 16; ++k)
             umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+          if (MC) umma_commit_mc(&empty[stage], (uint16_t)3);   // frees the stage in both CTAs (count 2)
+          else umma_commit(&empty[stage]);
           if (++stage == t.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[buf]);
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
     unsigned char* stg = epi_stage + (size_t)warp * kEpiWarpBytes;
     for (int64_t it = 0; it < my_items; ++it) {
       const int64_t item = first + it * stride;
-      const int m_tile = (int)(item / t.n_pass), pass = (int)(item % t.n_pass);
+      const int m_tile = tile_of(item), pass = (int)(item % t.n_pass);
       const int nb = pass_rows(t.N, pass, t.pw);
       const int n0 = pass * t.pw;
       const int buf = (int)(it & 1);
@@ -339,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or commit to its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1133,10 +1153,28 @@ static int launch_linear(const __half* X, const void* img, const float* bias, __
   if (stages > kMaxStages) stages = kMaxStages;
   t.stages = stages;
   const size_t smem = (size_t)stages * lin_stage_bytes() + tail + 1024;
-  RL_CUDA_CHECK(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Cluster multicast of the weight slices (two token tiles per cluster): on by default for the long-K layers
+  // whose weight pass cannot be resident; RL_XENC_MC=0 switches it off (A/B).
+  const char* mc_env = getenv("RL_XENC_MC");
+  const bool mc = (mc_env == nullptr || atoi(mc_env) != 0) && t.cp_async && T > kTileM && sm_count >= 2 &&
+                  (((N + t.pw - 1) / t.pw == N / t.pw) && (t.pw * 128) % 32 == 0);
+  if (mc) {
+    RL_CUDA_CHECK(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t units = (int64_t)(((T + kTileM - 1) / kTileM + 1) / 2) * t.n_pass;
+    const int clusters = (int)(units < sm_count / 2 ? units : sm_count / 2);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    RL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<true>, t));
+    return RL_OK;
+  }
+  RL_CUDA_CHECK(cudaFuncSetAttribute(linear_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t items = (int64_t)((T + kTileM - 1) / kTileM) * t.n_pass;
   const int grid = (int)(items < sm_count ? items : sm_count);
-  linear_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(t);
+  linear_tcgen05_kernel<false><<<grid, kThreads, smem, stream>>>(t);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
 }
