@@ -1153,10 +1153,11 @@ static int launch_linear(const __half* X, const void* img, const float* bias, __
   if (stages > kMaxStages) stages = kMaxStages;
   t.stages = stages;
   const size_t smem = (size_t)stages * lin_stage_bytes() + tail + 1024;
-  // Cluster multicast of the weight slices (two token tiles per cluster): on by default for the long-K layers
-  // whose weight pass cannot be resident; RL_XENC_MC=0 switches it off (A/B).
+  // Cluster multicast of the weight slices (two token tiles per cluster).  Validated bit-identical, measured no
+  // gain on B200 (FFN-down 89.9 us vs 88.6 us without, tools/time_linear.py): at cluster size 2 L2 already merges
+  // the two CTAs' unicast requests for the same lines, so the multicast removes no traffic.  Opt-in: RL_XENC_MC=1.
   const char* mc_env = getenv("RL_XENC_MC");
-  const bool mc = (mc_env == nullptr || atoi(mc_env) != 0) && t.cp_async && T > kTileM && sm_count >= 2 &&
+  const bool mc = (mc_env != nullptr && atoi(mc_env) != 0) && t.cp_async && T > kTileM && sm_count >= 2 &&
                   (((N + t.pw - 1) / t.pw == N / t.pw) && (t.pw * 128) % 32 == 0);
   if (mc) {
     RL_CUDA_CHECK(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -28,7 +28,7 @@ for name, N, K, act in shapes:
     if act:
         ref = torch.nn.functional.gelu(ref)
     Y = torch.empty((T, N), dtype=torch.float16, device="cuda")
-    for mode, (res, cpa, mc) in {"resident": ("1", "1", "1"), "stream_multicast": ("0", "1", "1"), "stream_cpasync": ("0", "1", "0"),
+    for mode, (res, cpa, mc) in {"resident": ("1", "1", "0"), "stream_multicast": ("0", "1", "1"), "stream_cpasync": ("0", "1", "0"),
                                  "stream_ring": ("0", "0", "0")}.items():
         os.environ["RL_XENC_RESIDENT"], os.environ["RL_XENC_CPASYNC"], os.environ["RL_XENC_MC"] = res, cpa, mc
         Y.zero_()
