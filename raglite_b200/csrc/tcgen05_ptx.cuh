@@ -131,6 +131,12 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
   return v;
 }
 
+// Warpgroup register reallocation (all four warps of a warpgroup execute the same instruction).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- thread-block-cluster / cta_group::2 helpers ------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

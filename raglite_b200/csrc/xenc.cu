@@ -76,7 +76,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // MiniLM shapes: K = 384, N = 1152 / 384 / 1536) use 192-column passes: the whole K extent of such a pass
 // (192 x 384 fp16 = 144 KB) stays RESIDENT in shared memory while the CTA walks the token tiles
 // (linear_wres_kernel).  Everything else streams 256-column weight slices (linear_tcgen05_kernel).
-constexpr int kResN = 128;
+constexpr int kResN = 192;
 constexpr int kResMaxKs = 6;
 __host__ __device__ inline bool use_resident(int N, int K) { return K % kSliceK == 0 && K / kSliceK <= kResMaxKs && N % kResN == 0; }
 __host__ __device__ inline int pass_width(int N, int K) { return use_resident(N, K) ? kResN : kMaxN; }
@@ -374,9 +374,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tcgen05_kernel(const LinAr
 // traffic per tile from 288 KB (activations + a 256-column weight slice per tile) to 96 KB and frees the
 // eight loader warps: twelve epilogue warps (three per TMEM lane quarter, two 32-column chunks each) now
 // drain a 128 x 192 accumulator while the next tile's MMAs run into the other TMEM buffer.
-// Pass width 128 (was 192): the resident weights shrink to 96 KB, which buys SIX activation stages -- a whole
-// 128-token tile of TMA loads in flight.  With 192 columns only three 16 KB stages fitted and the kernel waited
-// two load latencies per tile (3.4 us per tile against 1.2 us of MMA).
+// Pass width 192, three activation stages.  (kResN = 128 -- 96 KB of resident weights, SIX stages, a whole token
+// tile of TMA loads in flight -- was measured and is slower: QKV 58.1 vs 61.5 us, but out-proj 24.7 vs 22.7 and
+// FFN-up 105.4 vs 90.2: the deeper prefetch does not pay for re-reading the activations 1.5x as often.)
 constexpr int kResEpiWarps = kResN == 128 ? 8 : 12;   // two 32-column chunks per warp either way
 constexpr int kResProdWarp = kResEpiWarps;
 constexpr int kResMmaWarp = kResEpiWarps + 1;
@@ -384,7 +384,7 @@ constexpr int kResThreads = (kResEpiWarps + 2) * 32;
 constexpr int kResStages = kResN == 128 ? 6 : 3;
 constexpr int kResChunkStride = (kResEpiWarps / 4) * 32;   // columns between a warp's two chunks
 static_assert(kResN / 32 == 2 * (kResEpiWarps / 4), "two chunks per epilogue warp");
-constexpr uint32_t kResWSliceBytes = kResN * 128u;                    // one K slice of the pass: 16 KB
+constexpr uint32_t kResWSliceBytes = kResN * 128u;                    // one K slice of the pass: 24 KB
 constexpr uint32_t kResEpiBytes = kResEpiWarps * kEpiWarpBytes;
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
