@@ -35,23 +35,12 @@ using namespace tc;
 constexpr int kTileM = 128;           // corpus rows per tile (UMMA M)
 constexpr int kSliceK = 64;           // fp16 elements per K slice = one 128-byte swizzle row
 constexpr int kMaxQ = 256;            // queries per pass (UMMA N <= 256)
-// Warp roles, laid out by warpgroup (4 warps) because registers are (re)allocated per warpgroup:
-//   warps 0-3    epilogue (TMEM lane quarter == warp index)               128 registers
-//   warps 4-11   corpus loaders                                           160 registers (setmaxnreg.inc)
-//   warp 12 MMA issuer, warp 13 query producer, warps 14-15 idle           56 registers (setmaxnreg.dec)
-// The loaders hold the in-flight corpus loads in registers; what they can hold bounds the bytes in flight per SM
-// and with them the ingest rate at a given load latency (Little's law: two 32 KB items / ~1.5 us = 43 GB/s per
-// SM, 6.3 TB/s per chip -- the plateau every configuration sat on).  The 32 registers taken from the
-// MMA / producer warpgroup and given to each loader thread buy a third item in flight.
-constexpr int kNumEpiWarps = 4;
-constexpr int kFirstLoaderWarp = 4;
+constexpr int kNumEpiWarps = 4;       // warps 0..3 (TMEM lane quarter == warp index)
+constexpr int kMmaWarp = 4;
+constexpr int kQWarp = 5;
+constexpr int kFirstLoaderWarp = 6;
 constexpr int kNumLoaderWarps = 8;
-constexpr int kMmaWarp = 12;
-constexpr int kQWarp = 13;
-constexpr int kThreads = 16 * 32;     // 512
-constexpr int kLoaderRegs = 160, kLeanRegs = 56;
-constexpr int kRing = 3;              // fp32 corpus: K-slice items (32 KB each per SM) in flight in registers
-constexpr int kRing16 = 6;            // fp16 corpus: items of 16 KB
+constexpr int kThreads = (kFirstLoaderWarp + kNumLoaderWarps) * 32;  // 448
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kTileM * 128;  // 16 KB per stage
 constexpr uint32_t kSmemBudget = 222 * 1024;
@@ -116,7 +105,7 @@ __host__ __device__ inline uint32_t tail_bytes(int n_groups) {
 // EF16: the corpus is stored as fp16 (lossless for RAGLite data, whose embeddings are fp16-rounded,
 // reference _embed.py:140): rows are copied into the swizzled tile without conversion, half the HBM bytes.
 template <int METRIC, bool PAIR, bool EF16>
-__global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs t) {
+__global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   // Group-parallel mode (B > 256, the default): the CTAs of a "lane" -- par_groups consecutive CTAs -- walk the
   // SAME corpus tiles at the same time, one 256-query group each.  The first of them pulls a tile in from
@@ -220,17 +209,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
   if (PAIR) cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_ptr;
-  // Register reallocation by warpgroup happens at the top of each role branch (the instruction must dominate the
-  // code that uses the registers; the .inc waits until the .dec of the lean warpgroup has freed some).
   // Cosine on a corpus whose rows all have norm >= 0.5 and moderate magnitudes (the normal case:
   // embeddings are stored normalised): rows go to fp16 unscaled and the epilogue applies 1/|e|.
   const bool cos_noscale = METRIC == RL_METRIC_COSINE &&
                            (EF16 || (t.row_stats[2] > 0.f && t.row_stats[2] <= 2.f && t.row_stats[1] <= 1024.f &&
                                      t.row_stats[3] == 0.f));   // (the host only allows fp16 storage when this holds)
 
-  const bool is_loader = warp >= kFirstLoaderWarp && warp < kFirstLoaderWarp + kNumLoaderWarps;
-  if (EF16 && is_loader) {
-    setmaxnreg_inc<kLoaderRegs>();
+  if (EF16 && warp >= kFirstLoaderWarp) {
     // ===== corpus loaders, fp16 storage: HBM -> registers -> swizzled smem, no conversion =====
     // A K slice of a row is 128 bytes = 8 chunks of 16 bytes; thread lt owns chunk lt & 7 of rows
     // (lt >> 3) + 32 i.  Four items (4 x 16 KB per SM) stay in flight in registers.
@@ -243,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
     const int64_t total_items = v_tiles * t.n_ks;
     const size_t pitch32_bytes = (size_t)a.ld * 32 * sizeof(__half);
     const size_t slice_bytes = kSliceK * sizeof(__half);
-    uint4 ring[kRing16][4];
+    uint4 ring[4][4];
     int64_t ld_tile = 0;
     int ld_ks = 0, ld_rows = 0;
     const unsigned char* ld_ptr = nullptr;
@@ -322,14 +307,14 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
     pf_set_tile();
     for (int i = 0; i < 2 * kPrefetchItems; ++i) prefetch_item();
 #pragma unroll
-    for (int r = 0; r < kRing16; ++r) issue_item(ring[r]);
-    for (int64_t item = 0; item < total_items; item += kRing16) {
-#pragma unroll
-      for (int r = 0; r < kRing16; ++r)
-        if (item + r < total_items) process(ring[r]);
+    for (int r = 0; r < 4; ++r) issue_item(ring[r]);
+    for (int64_t item = 0; item < total_items; item += 4) {
+      process(ring[0]);
+      if (item + 1 < total_items) process(ring[1]);
+      if (item + 2 < total_items) process(ring[2]);
+      if (item + 3 < total_items) process(ring[3]);
     }
-  } else if (is_loader) {
-    setmaxnreg_inc<kLoaderRegs>();
+  } else if (warp >= kFirstLoaderWarp) {
     // ===== corpus loaders: HBM fp32 -> registers -> fp16 -> swizzled smem (UMMA A operand) =====
     const int lt = threadIdx.x - kFirstLoaderWarp * 32;  // 0..255
     const int c4 = lt & 15;                              // float4 column within the 64-wide K slice
@@ -339,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
     // cosine 1/|e| then moves to the epilogue, which has slack; dot/l2: the global scale is 1).
     const bool noscale = (METRIC == RL_METRIC_COSINE) ? cos_noscale : (gscale == 1.f);
     const int64_t total_items = v_tiles * t.n_ks;
-    float4 ring[kRing][8];
+    float4 ring[2][8];
     float rs[8];
 
     // Incremental cursors (no integer divisions or multiplies on the hot path).  `ld_*` runs two items
@@ -468,16 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
     ld_set_tile();
     pf_set_tile();
     for (int i = 0; i < kPrefetchItems; ++i) prefetch_item();
-#pragma unroll
-    for (int r = 0; r < kRing; ++r) issue_item(ring[r]);
-    for (int64_t item = 0; item < total_items; item += kRing) {
-#pragma unroll
-      for (int r = 0; r < kRing; ++r)
-        if (item + r < total_items) process(ring[r]);
+    issue_item(ring[0]);
+    issue_item(ring[1]);
+    for (int64_t item = 0; item < total_items; item += 2) {
+      process(ring[0]);
+      if (item + 1 < total_items) process(ring[1]);
     }
-  } else if (warp >= kMmaWarp) {
-   setmaxnreg_dec<kLeanRegs>();   // warps 12-15: MMA issuer, query producer, two idle warps
-   if (warp == kQWarp) {
+  } else if (warp == kQWarp) {
     // ===== query producer: bulk-copy the pre-swizzled fp16 K slice of all queries (UMMA B operand) =====
     if (lane == 0) {
       // Group g's image starts g * (n_ks * kMaxQ * kSliceK) halves into qimg; inside a group the K slices of
@@ -499,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
         if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     }
-   } else if (warp == kMmaWarp) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (PAIR && rank != 0) {
       // Peer CTA: no MMA issue.  Relay "my A tile and my half of the queries are in place" to the
@@ -552,8 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
         else umma_commit(&s.tmem_full[buf]);
       }
     }
-   }
-  } else if (warp < kNumEpiWarps) {
+  } else {
     // ===== epilogue warps 0..3: TMEM -> registers -> key -> dump / threshold + emit =====
     const int q = warp;  // TMEM lane quarter
     bool flushed_once = false;
@@ -749,6 +730,413 @@ __global__ void __launch_bounds__(kThreads, 1) scan_tcgen05_kernel(const TcArgs 
   }
 }
 
+// ---- DUAL: two corpus tiles per query slice ------------------------------------------------------------------
+// Measured (round 2, ncu + batch sweep): with the corpus in HBM, a step costs the HBM time of the corpus plus
+// ~0.055 ms per GB of QUERY image the SMs pull from L2 -- the image is re-streamed for every 128-row tile, 61 GB
+// per step at B = 256, as much as the corpus itself.  This variant lets a CTA hold TWO corpus tiles per K slice
+// and issue both MMAs (M = 128 each) against ONE copy of the query slice: the L2 -> SM query stream halves.
+// The two accumulators take all 512 TMEM columns, so the epilogue of a tile pair does not overlap the MMAs
+// of the next pair (the smem stages keep filling while it lasts).  One group of <= 256 queries per CTA
+// (B > 256 runs group-parallel lanes).
+//
+// Stage: [A tile 0 16 KB | A tile 1 16 KB | query slice nq * 128 B].  Same 14 warps as the single-tile kernel:
+// 0-3 epilogue (both tiles, one after the other; TMEM lane quarter = warp), 4 MMA issuer, 5 query producer,
+// 6-13 corpus loaders.  (Registers are allocated per 128 threads: a 576-thread block with four more epilogue
+// warps would be held to 96 registers per thread -- the probe in tools/probe_attrs.py shows it.)
+constexpr int kDualEpiWarps = kNumEpiWarps;
+constexpr int kDualMmaWarp = kMmaWarp;
+constexpr int kDualQWarp = kQWarp;
+constexpr int kDualFirstLoader = kFirstLoaderWarp;
+constexpr int kDualThreads = kThreads;   // 448
+__host__ __device__ inline uint32_t dual_stage_bytes(int nq) { return 2u * kABytes + (uint32_t)nq * 128u; }
+__device__ __forceinline__ void epi_bar_sync_dual() { epi_bar_sync(); }
+
+template <int METRIC, bool EF16>
+__global__ void __maxnreg__(128) scan_tcgen05_dual_kernel(const TcArgs t) {
+  extern __shared__ unsigned char smem_dyn[];
+  const int P = t.par_groups > 1 ? t.par_groups : 1;
+  const int pg = P > 1 ? (int)(blockIdx.x % (unsigned)P) : 0;
+  ScanArgs a = t.a;
+  const float* q_scale_g = t.q_scale;
+  const __half* qimg_g = t.qimg;
+  int nq = t.nq_last;                    // padded width of the group this CTA serves
+  if (P > 1) {
+    const int q0p = pg * kMaxQ;
+    a.B = min(kMaxQ, t.a.B - q0p);
+    a.thr += q0p; a.cand_cnt += q0p; a.eps += q0p; a.hist_inv_w += q0p; a.q_inv_norm += q0p;
+    if (a.cnt_all != nullptr) a.cnt_all += q0p;
+    a.dump += (size_t)q0p * a.n_sample_rows;
+    a.cand += (size_t)q0p * a.cap;
+    a.ghist += (size_t)q0p * kHistBins;
+    q_scale_g += q0p;
+    qimg_g += (size_t)pg * t.n_ks * kMaxQ * kSliceK;
+    nq = (pg == P - 1) ? t.nq_last : t.nq;
+  }
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const uint32_t sbytes = dual_stage_bytes(t.nq);
+  SmemLayout s;
+  s.stage_base = base;
+  s.full = reinterpret_cast<uint64_t*>(base + (size_t)t.stages * sbytes);
+  s.empty = s.full + kMaxStages;
+  s.tmem_full = s.empty + kMaxStages;
+  s.tmem_empty = s.tmem_full + 2;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_empty + 2);
+  s.thr = reinterpret_cast<float*>(s.tmem_ptr + 4);
+  s.cs = s.thr + kMaxQ;
+  s.thr0 = s.cs + kMaxQ;
+  s.inv_w = s.thr0 + kMaxQ;
+  s.hist = reinterpret_cast<uint32_t*>(s.inv_w + kMaxQ);
+  s.cnt = reinterpret_cast<int*>(s.hist + kMaxQ * kHistBins / 2);
+  s.basev = s.cnt + kMaxQ;
+  s.list_n = s.basev + kMaxQ;
+  s.list = reinterpret_cast<uint32_t*>(s.list_n + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Work units: pairs of consecutive block ordinals (2u, 2u + 1); a missing second block is an empty tile.
+  const int64_t n_units = (a.n_mode_blocks + 1) / 2;
+  const int64_t first = (int64_t)blockIdx.x / P, stride = (int64_t)gridDim.x / P;
+  const int64_t my_units = first < n_units ? (n_units - first + stride - 1) / stride : 0;
+  auto ord_of = [&](int64_t unit, int half) -> int64_t { return 2 * (first + unit * stride) + half; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < t.stages; ++i) {
+      mbar_init(&s.full[i], 2 * kNumLoaderWarps + 1);   // 8 loader warps x 2 tiles + the query producer (expect_tx)
+      mbar_init(&s.empty[i], 1);                         // one tcgen05.commit
+    }
+    mbar_init(&s.tmem_full[0], 1);
+    mbar_init(&s.tmem_empty[0], kDualEpiWarps);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < kMaxQ; i += blockDim.x) {
+    s.thr[i] = (i < a.B && !a.dump_mode) ? a.thr[i] : __int_as_float(0x7f800000);  // +inf: never emit
+    s.cs[i] = (i < a.B) ? q_scale_g[i] : 0.f;
+    s.cnt[i] = 0;
+    s.thr0[i] = s.thr[i];
+    s.inv_w[i] = (i < a.B && !a.dump_mode) ? a.hist_inv_w[i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kMaxQ * kHistBins / 2; i += blockDim.x) s.hist[i] = 0u;
+  if (threadIdx.x == 0) { s.list_n[0] = 0; s.list_n[1] = 0; }
+  if (warp == kDualMmaWarp) tmem_alloc(s.tmem_ptr, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_ptr;
+  // (the launcher only picks this kernel when rows need no per-row scaling in the loader: cosine on a
+  // normalised corpus -- 1/|e| is applied in the epilogue -- or dot / l2 with their global power of two)
+  const int64_t total_items = my_units * t.n_ks * 2;   // loader items: (unit, K slice, tile half)
+
+  if (warp >= kDualFirstLoader) {
+    const int lt = threadIdx.x - kDualFirstLoader * 32;  // 0..255
+    const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
+    const bool scale = gscale != 1.f;
+    // Per-thread geometry.  fp32 storage: float4 column c4 of rows r0 + 16 i (i < 8); fp16: 16-byte chunk j of
+    // rows r0 + 32 i (i < 4).  Both move 16 KB (one tile's K slice) per item.
+    const int c4 = lt & 15, r0f = lt >> 4;
+    const int j = lt & 7, r0h = lt >> 3;
+    const size_t esz = EF16 ? sizeof(__half) : sizeof(float);
+    const size_t slice_bytes = kSliceK * esz;
+    const size_t row_pitch = (size_t)a.ld * esz;
+    const unsigned char* Eb = reinterpret_cast<const unsigned char*>(a.E);
+    const uint32_t sw_f = (uint32_t)r0f * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r0f & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+    const uint32_t sw_h = (uint32_t)r0h * 128u + (((uint32_t)j ^ ((uint32_t)r0h & 7u)) << 4);
+    // cursors: ld_* two items ahead of the stores, pf_* kPrefetchItems further ahead (L2 only)
+    struct Cur { int unit, ks, half, rows0, rows1; const unsigned char *p0, *p1; };
+    auto set_unit = [&](Cur& c, int thread_row, size_t col_bytes) {
+      c.rows0 = c.rows1 = 0;
+      if ((int64_t)c.unit < my_units) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t ord = ord_of((int64_t)c.unit, h);
+          if (ord < a.n_mode_blocks) {
+            const int64_t blk = mode_block_index(a, ord);
+            const int64_t rem = a.n_rows - blk * kTileM;
+            const int rows = rem < kTileM ? (int)rem : kTileM;
+            const unsigned char* p = Eb + (size_t)(blk * kTileM + thread_row) * row_pitch + col_bytes;
+            if (h == 0) { c.rows0 = rows; c.p0 = p; } else { c.rows1 = rows; c.p1 = p; }
+          }
+        }
+      }
+    };
+    auto advance = [&](Cur& c, int thread_row, size_t col_bytes) {
+      if (c.half == 0) c.p0 += slice_bytes; else c.p1 += slice_bytes;
+      c.half ^= 1;
+      if (c.half == 0 && ++c.ks == t.n_ks) { c.ks = 0; ++c.unit; set_unit(c, thread_row, col_bytes); }
+    };
+    Cur ld{0, 0, 0, 0, 0, nullptr, nullptr}, pf{0, 0, 0, 0, 0, nullptr, nullptr};
+    const int ld_row = EF16 ? r0h : r0f;
+    const size_t ld_col = EF16 ? (size_t)j * 16 : (size_t)c4 * 16;
+    const int pf_row = EF16 ? (lt & 127) : (lt >> 1);
+    const size_t pf_col = EF16 ? 0 : (size_t)(lt & 1) * 128;
+    auto prefetch_item = [&]() {   // one 128-byte line per thread (fp32: 2 lines per row slice, fp16: 1)
+      const int rows = pf.half ? pf.rows1 : pf.rows0;
+      const unsigned char* p = pf.half ? pf.p1 : pf.p0;
+      const bool active = EF16 ? lt < 128 : true;
+      if (pg == 0 && active && pf_row < rows && (size_t)pf.ks * slice_bytes + pf_col < (size_t)a.d * esz) prefetch_l2(p);
+      advance(pf, pf_row, pf_col);
+    };
+    uint4 ring[2][8];   // fp32: 8 x 16 B per item; fp16 uses the first 4
+    auto issue_item = [&](uint4 (&buf)[8]) {
+      const int rows = ld.half ? ld.rows1 : ld.rows0;
+      const unsigned char* p = ld.half ? ld.p1 : ld.p0;
+      const bool col_ok = (size_t)ld.ks * slice_bytes + ld_col < (size_t)a.d * esz;
+      if (EF16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          buf[i] = (col_ok && r0h + 32 * i < rows) ? ldg_stream_u4(p) : make_uint4(0u, 0u, 0u, 0u);
+          p += 32 * row_pitch;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          buf[i] = (col_ok && r0f + 16 * i < rows) ? ldg_stream_u4(p) : make_uint4(0u, 0u, 0u, 0u);
+          p += 16 * row_pitch;
+        }
+      }
+      advance(ld, ld_row, ld_col);
+      prefetch_item();
+    };
+    int stage = 0, st_half = 0;
+    uint32_t phase = 0;
+    const __half2 gs2 = __float2half2_rn(gscale);
+    auto process = [&](uint4 (&buf)[8]) {
+      mbar_wait(&s.empty[stage], phase ^ 1u);   // (second tile of a stage: same phase, passes at once)
+      unsigned char* A = s.stage_base + (size_t)stage * sbytes + (size_t)st_half * kABytes;
+      if (EF16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v = buf[i];
+          if (scale) {
+            __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gs2);
+          }
+          *reinterpret_cast<uint4*>(A + sw_h + i * 32 * 128) = v;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 f = *reinterpret_cast<const float4*>(&buf[i]);
+          const __half2 h01 = scale ? __floats2half2_rn(f.x * gscale, f.y * gscale) : __floats2half2_rn(f.x, f.y);
+          const __half2 h23 = scale ? __floats2half2_rn(f.z * gscale, f.w * gscale) : __floats2half2_rn(f.z, f.w);
+          uint2 packed;
+          packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+          packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(A + sw_f + i * 16 * 128) = packed;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[stage]);
+      issue_item(buf);
+      st_half ^= 1;
+      if (st_half == 0 && ++stage == t.stages) { stage = 0; phase ^= 1u; }
+    };
+    set_unit(ld, ld_row, ld_col);
+    set_unit(pf, pf_row, pf_col);
+    for (int i = 0; i < kPrefetchItems; ++i) prefetch_item();
+    issue_item(ring[0]);
+    issue_item(ring[1]);
+    for (int64_t item = 0; item < total_items; item += 2) {
+      process(ring[0]);
+      if (item + 1 < total_items) process(ring[1]);
+    }
+  } else if (warp == kDualQWarp) {
+    if (lane == 0) {
+      const uint32_t qbytes = (uint32_t)nq * 128u;   // one K slice of the group's queries
+      const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(qimg_g);
+      const int64_t n_stages_total = my_units * t.n_ks;
+      int ks = 0, stage = 0;
+      uint32_t phase = 0;
+      for (int64_t it = 0; it < n_stages_total; ++it) {
+        mbar_wait(&s.empty[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&s.full[stage], qbytes);
+        bulk_g2s(s.stage_base + (size_t)stage * sbytes + 2 * kABytes, qsrc + (size_t)ks * qbytes, qbytes, &s.full[stage]);
+        if (++ks == t.n_ks) ks = 0;
+        if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == kDualMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kTileM, nq);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t u = 0; u < my_units; ++u) {
+        mbar_wait(&s.tmem_empty[0], (uint32_t)((u & 1) ^ 1));   // both accumulators drained by the 8 epilogue warps
+        tc_fence_after();
+        const uint32_t d0 = tmem_base, d1 = tmem_base + (uint32_t)t.buf_cols;
+        for (int ks = 0; ks < t.n_ks; ++ks) {
+          mbar_wait(&s.full[stage], phase);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.stage_base + (size_t)stage * sbytes);
+          const uint64_t a0 = make_kmajor_sw128_desc(a_addr), a1 = make_kmajor_sw128_desc(a_addr + kABytes);
+          const uint64_t b = make_kmajor_sw128_desc(a_addr + 2 * kABytes);
+#pragma unroll
+          for (int k = 0; k < kSliceK / 16; ++k) {
+            umma_f16(d0, a0 + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_f16(d1, a1 + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&s.empty[stage]);
+          if (++stage == t.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&s.tmem_full[0]);
+      }
+    }
+  } else {
+    // ===== epilogue warps 0..3 (TMEM lane quarter = warp): tile 0, then tile 1 of the pair =====
+    const int q = warp;
+    const bool cos_noscale = METRIC == RL_METRIC_COSINE;
+    bool flushed_once = false;
+    for (int64_t u = 0; u < my_units; ++u) {
+     mbar_wait(&s.tmem_full[0], (uint32_t)(u & 1));
+     tc_fence_after();
+     for (int half = 0; half < 2; ++half) {
+      const int64_t ord = ord_of(u, half);
+      const bool has_block = ord < a.n_mode_blocks;
+      const int64_t blk = has_block ? mode_block_index(a, ord) : 0;
+      const int r_in = q * 32 + lane;
+      const int64_t row = blk * kTileM + r_in;
+      bool valid = has_block && row < a.n_rows;
+      bool masked_alive = false;
+      if (valid && a.row_allowed != nullptr) {
+        valid = a.row_allowed[row] != 0;
+        if (!valid && a.cnt_all != nullptr) masked_alive = a.row_alive == nullptr || a.row_alive[row] != 0;
+      }
+      const float bias = (METRIC == RL_METRIC_L2 && valid) ? -a.sq_norm[row] : 0.f;
+      const float lane_scale = (cos_noscale && valid) ? __ldg(a.inv_norm + row) : 1.f;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * t.buf_cols);
+      for (int c0 = 0; c0 < nq; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32_async(taddr0 + (uint32_t)c0, v);
+        tmem_ld_wait(v);
+        if (a.dump_mode) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int col = c0 + jj;
+            if (col < a.B) {
+              float key = __uint_as_float(v[jj]);
+              if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
+              else key *= lane_scale;
+              if (has_block) a.dump[(size_t)col * a.n_sample_rows + ord * kTileM + r_in] = valid ? key : kNegInf;
+            }
+          }
+        } else {
+          uint32_t mask = 0;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            float key = __uint_as_float(v[jj]);
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[c0 + jj], bias);
+            else key *= lane_scale;
+            if (key >= s.thr[c0 + jj]) mask |= 1u << jj;
+          }
+          if (masked_alive) {
+            uint32_t extra = mask;
+            while (extra != 0) {
+              const int jj = __ffs(extra) - 1;
+              extra &= extra - 1;
+              atomicAdd(a.cnt_all + c0 + jj, 1);
+            }
+          }
+          if (!valid) mask = 0;
+          while (mask != 0) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int col = c0 + jj;
+            float key = __uint_as_float(select32(v, jj));
+            if (METRIC != RL_METRIC_COSINE) key = fmaf(key, s.cs[col], bias);
+            else key *= lane_scale;
+            const int pos = atomicAdd(&s.list_n[0], 1);
+            const int hb = col * kHistBins + hist_bin(key, s.thr0[col], s.inv_w[col]);
+            atomicAdd(&s.hist[hb >> 1], 1u << ((hb & 1) * 16));
+            if (pos < kListCap) {
+              s.list[pos * 3 + 0] = (uint32_t)col;
+              s.list[pos * 3 + 1] = __float_as_uint(key);
+              s.list[pos * 3 + 2] = (uint32_t)row;
+            } else {
+              emit_candidate(a, col, key, (int32_t)row);
+            }
+          }
+        }
+      }
+     }   // half
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.tmem_empty[0]);   // both accumulators are free once the 4 warps have arrived
+      if (!a.dump_mode) {
+        constexpr int NT = kDualEpiWarps * 32;
+        const int et = threadIdx.x;  // 0..255
+        epi_bar_sync_dual();
+        const int n_all = s.list_n[0];
+        epi_bar_sync_dual();
+        const bool last = u + 1 == my_units;
+        const bool do_flush = n_all >= (flushed_once ? kFlushAt : kFlushFirst) || (last && n_all > 0);
+        if (do_flush) {
+          flushed_once = true;
+          const int n = min(n_all, kListCap);
+          for (int e = et; e < n; e += NT) {
+            const int col = (int)s.list[e * 3 + 0];
+            s.list[e * 3 + 0] = (uint32_t)col | ((uint32_t)atomicAdd(&s.cnt[col], 1) << 16);
+          }
+          epi_bar_sync_dual();
+          for (int col = et; col < kMaxQ; col += NT) {
+            const int c = s.cnt[col];
+            if (c > 0) {
+              s.basev[col] = atomicAdd(a.cand_cnt + col, c);
+              s.cnt[col] = 0;
+            }
+          }
+          for (int w = et; w < kMaxQ * kHistBins / 2; w += NT) {
+            const uint32_t h = s.hist[w];
+            if (h != 0u) {
+              if (h & 0xFFFFu) atomicAdd(a.ghist + 2 * w, (int)(h & 0xFFFFu));
+              if (h >> 16) atomicAdd(a.ghist + 2 * w + 1, (int)(h >> 16));
+              s.hist[w] = 0u;
+            }
+          }
+          epi_bar_sync_dual();
+          if (et == 0) s.list_n[0] = 0;
+          for (int e = et; e < n; e += NT) {
+            const uint32_t w0 = s.list[e * 3 + 0];
+            const int col = (int)(w0 & 0xFFFFu);
+            const int slot = s.basev[col] + (int)(w0 >> 16);
+            if (slot < a.cap)
+              a.cand[(size_t)col * a.cap + slot] = Cand{__uint_as_float(s.list[e * 3 + 1]), (int32_t)s.list[e * 3 + 2]};
+          }
+        }
+        const bool periodic = (u % (kRefreshEvery / 2)) == kRefreshEvery / 2 - 1;   // a unit is two tiles
+        if ((do_flush || periodic) && !last) {
+          for (int col = et; col < a.B; col += NT) {
+            const int4* gh = reinterpret_cast<const int4*>(a.ghist + (size_t)col * kHistBins);
+            int cnts[kHistBins];
+#pragma unroll
+            for (int q4 = 0; q4 < kHistBins / 4; ++q4) {
+              const int4 v4 = __ldcg(gh + q4);
+              cnts[4 * q4] = v4.x; cnts[4 * q4 + 1] = v4.y; cnts[4 * q4 + 2] = v4.z; cnts[4 * q4 + 3] = v4.w;
+            }
+            int cum = 0, best = -1;
+#pragma unroll
+            for (int bb = kHistBins - 1; bb >= 1; --bb) {
+              cum += cnts[bb];
+              if (best < 0 && cum >= a.sel_count) best = bb;
+            }
+            if (best >= 1 && s.inv_w[col] > 0.f) {
+              const float nt = s.thr0[col] + (float)best / s.inv_w[col] - 2.f * a.eps[col];
+              if (nt > s.thr[col]) s.thr[col] = nt;
+            }
+          }
+        }
+        if (do_flush || periodic) epi_bar_sync_dual();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kDualMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
 // Query image: fp16, scaled, laid out exactly as the swizzled smem stage rows.
 __global__ void __launch_bounds__(128) query_image_kernel(const float* __restrict__ Q, int B, int d, int metric,
                                                           const float* __restrict__ q_inv_norm,
@@ -860,11 +1248,19 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     int cols = 32;
     while (cols < 2 * t.buf_cols) cols *= 2;
     t.tmem_cols = cols;
-    // cta_group::2 (SM pair) variant: validated bit-identical, but measured SLOWER than one CTA per SM on
-    // B200 (15.1 ms vs 12.6 ms on the 61 GB shard, same box: the peer->leader barrier relay and the
-    // coupling of two SMs cost more than the halved query stream saves), so it is opt-in: RL_TC_PAIR=1.
-    static const int pair_env = []() { const char* e = getenv("RL_TC_PAIR"); return e ? atoi(e) : 0; }();
-    const bool pair = pair_env == 1 && t.nq % 32 == 0 && t.nq_last % 32 == 0 && t.nq_last >= 64 && a_in.n_mode_blocks >= 2 &&
+    // cta_group::2 (SM pair): the two CTAs of a cluster issue ONE M = 256 MMA per K step and each holds only half
+    // of the query slice, so an SM pulls 16 KB instead of 32 KB of query image per stage from L2 (the L2 -> SM
+    // stream: -25 % on an fp32 corpus, -33 % on fp16).  Default for a single query group (B <= 256) since the
+    // cluster-scope barrier operations left its hot loop: `mbarrier.arrive.release.cluster` compiles to
+    // MEMBAR.ALL.GPU + ERRBAR and `try_wait.acquire.cluster` to CCTL.IVALL, and the peer's per-stage relay
+    // thread paid that membar on every K slice -- 0.96 us per slice, the 15.4 ms this variant first measured
+    // against 12.4 ms for one CTA per SM.  With default-scope barrier operations (what CUTLASS's ClusterBarrier
+    // uses): 61 GB fp32 shard 11.87 vs 12.80 ms, fp16 shard 8.20 vs 8.67 ms, same box, back to back.  Group-parallel
+    // lanes (B > 256) do not gain (23.6 vs 23.1 ms: 74 clusters / 4 groups leave 4 SMs idle) and keep one CTA per
+    // SM unless RL_TC_PAIR=1 forces pairs; RL_TC_PAIR=0 turns them off everywhere.
+    static const int pair_env = []() { const char* e = getenv("RL_TC_PAIR"); return e ? atoi(e) : -1; }();
+    const bool pair_wanted = pair_env == 1 || (pair_env < 0 && ng == 1);
+    const bool pair = pair_wanted && t.nq % 32 == 0 && t.nq_last % 32 == 0 && t.nq_last >= 64 && a_in.n_mode_blocks >= 2 &&
                       sm_count >= 2;
     const uint32_t avail = kSmemBudget - 1024 - tail_bytes(t.n_groups);
     int stages = (int)(avail / stage_bytes(pair ? t.nq / 2 : t.nq));
@@ -897,6 +1293,38 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     };
     int rc;
     const bool f16 = p->e_dtype == 1;
+    // Two corpus tiles per query slice (halves the L2 -> SM query stream): one query group per CTA, rows that
+    // need no per-row scaling in the loader.  Validated (the whole -m gpu suite passes with it) but measured
+    // SLOWER on B200 than the single-tile kernel, same box, back to back: 61 GB fp32 shard 14.1 vs 12.4 ms,
+    // fp16 shard 8.95 vs 8.81 ms, configs[2] 30.2 vs 21.6 ms -- with both accumulators live the epilogue no
+    // longer overlaps the next tile's MMAs and only three smem stages fit, which costs more than the halved
+    // query stream saves.  Opt-in: RL_TC_DUAL=1.
+    static const int dual_env = []() { const char* e = getenv("RL_TC_DUAL"); return e ? atoi(e) : 0; }();
+    const bool dual = dual_env == 1 && !pair && t.n_groups == 1 && a_in.n_mode_blocks >= 2 &&
+                      (p->metric != RL_METRIC_COSINE || p->rows_unit_scale == 1);
+    if (dual) {
+      const uint32_t avail_d = kSmemBudget - 1024 - tail_bytes(1);
+      int st = (int)(avail_d / dual_stage_bytes(t.nq));
+      if (st > kMaxStages) st = kMaxStages;
+      if (st >= 2) {
+        t.stages = st;
+        const size_t smem_d = (size_t)st * dual_stage_bytes(t.nq) + tail_bytes(1) + 1024;
+        auto launch_dual = [&](auto kernel) -> int {
+          RL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+          const int64_t n_units = (a_in.n_mode_blocks + 1) / 2;
+          const int lanes = sm_count / t.par_groups;
+          const unsigned grid = (unsigned)((n_units < lanes ? n_units : lanes) * t.par_groups);
+          kernel<<<grid, kDualThreads, smem_d, stream>>>(t);
+          RL_CUDA_CHECK(cudaGetLastError());
+          return RL_OK;
+        };
+        if (p->metric == RL_METRIC_COSINE) rc = f16 ? launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_COSINE, true>) : launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_COSINE, false>);
+        else if (p->metric == RL_METRIC_DOT) rc = f16 ? launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_DOT, true>) : launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_DOT, false>);
+        else rc = f16 ? launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_L2, true>) : launch_dual(scan_tcgen05_dual_kernel<RL_METRIC_L2, false>);
+        if (rc != RL_OK) return rc;
+        continue;
+      }
+    }
     auto dispatch = [&](auto metric_tag) -> int {
       constexpr int M = decltype(metric_tag)::value;
       if (pair) return f16 ? launch(scan_tcgen05_kernel<M, true, true>, true) : launch(scan_tcgen05_kernel<M, true, false>, true);
@@ -910,14 +1338,24 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
   return RL_OK;
 }
 
-// Debug probe: function attributes of the scan kernel as the driver sees them (tools/probe_attrs.py).
+// Debug probe: function attributes / occupancy of the scan kernels as the driver sees them.
 int debug_scan_kernel_attrs(int which, int* out) {
   cudaFuncAttributes fa;
   cudaError_t e = which == 0 ? cudaFuncGetAttributes(&fa, scan_tcgen05_kernel<0, false, false>)
-                             : cudaFuncGetAttributes(&fa, scan_tcgen05_kernel<0, false, true>);
+                             : (which == 1 ? cudaFuncGetAttributes(&fa, scan_tcgen05_dual_kernel<0, false>)
+                                           : cudaFuncGetAttributes(&fa, scan_tcgen05_dual_kernel<0, true>));
   if (e != cudaSuccess) return (int)e;
   out[0] = fa.numRegs; out[1] = fa.maxThreadsPerBlock; out[2] = (int)fa.sharedSizeBytes; out[3] = (int)fa.localSizeBytes;
-  out[4] = fa.maxDynamicSharedSizeBytes; out[5] = -1; out[6] = 0;
+  out[4] = fa.maxDynamicSharedSizeBytes;
+  int nb = -1;
+  const size_t smem = 224448;
+  if (which >= 1) {
+    cudaFuncSetAttribute(which == 1 ? (const void*)scan_tcgen05_dual_kernel<0, false> : (const void*)scan_tcgen05_dual_kernel<0, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = which == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tcgen05_dual_kernel<0, false>, kDualThreads, smem)
+                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, scan_tcgen05_dual_kernel<0, true>, kDualThreads, smem);
+  }
+  out[5] = nb; out[6] = (int)e;
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   out[7] = prop.regsPerBlock; out[8] = prop.regsPerMultiprocessor; out[9] = (int)prop.sharedMemPerBlockOptin;

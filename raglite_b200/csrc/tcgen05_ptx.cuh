@@ -153,14 +153,21 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
   return r;
 }
+// Remote arrive with the DEFAULT semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) does.
+// The `.release.cluster` form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive: about a
+// microsecond per call under load, which serialised the PAIR kernel's per-stage relay thread (0.96 us per K slice
+// = the 15.4 ms that variant measured).  What the arrive publishes is either "TMEM buffer drained" (ordered by
+// tcgen05.fence::before_thread_sync) or shared-memory stores that the arriving thread has already observed through
+// its own CTA's mbarrier and pushed to the async proxy with fence.proxy.async.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      // default acquire.cta: the `.acquire.cluster` form makes ptxas invalidate L1 (CCTL.IVALL) after every wait
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
