@@ -70,6 +70,7 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--sample-stride", type=int, default=0, help="override the sampling stride (0 = library heuristic)")
     ap.add_argument("--storage", default="fp32", choices=["fp32", "fp16"],
                     help="fp16: corpus rounded to float16 and stored as such (lossless layout for RAGLite data)")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight in the end-to-end loop (1: serial vector_search_batch calls)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=0)
@@ -705,15 +706,34 @@ def main() -> None:  # noqa: PLR0915
     cfg = rl.RAGLiteConfig(db_url=f"bench://rank{rank}", reranker=None, vector_search_query_adapter=use_adapter)
     rl.register_index(cfg, index)
 
-    def timed_e2e(**kw):  # noqa: ANN003, ANN202
-        for _ in range(2):
-            r = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
-                                       exact_maxsim=args.exact_maxsim, algo=args.algo, **kw)
+    def timed_e2e(inflight: int = 1, **kw):  # noqa: ANN003, ANN202
+        """K searches through the public API, host queries in -> host results out for every one of them.
+        inflight = 1: vector_search_batch, one call after the other (each waits for its result);
+        inflight > 1: vector_search_batch_async with that many batches in flight (each on its own stream with its own
+        upload, kernels and pinned download; results collected in order) -- how a server drives the index."""
+        from collections import deque
+
+        common = dict(num_results=k, oversample=args.oversample, config=cfg, exact_maxsim=args.exact_maxsim, algo=args.algo, **kw)
+
+        def run(n: int):  # noqa: ANN202
+            r = None
+            if inflight <= 1:
+                for _ in range(n):
+                    r = rl.vector_search_batch(Q_host, **common)
+                return r
+            pend: deque = deque()
+            for _ in range(n):
+                pend.append(rl.vector_search_batch_async(Q_host, **common))
+                if len(pend) >= inflight:
+                    r = pend.popleft().result()
+            while pend:
+                r = pend.popleft().result()
+            return r
+
+        run(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r = rl.vector_search_batch(Q_host, num_results=k, oversample=args.oversample, config=cfg,
-                                       exact_maxsim=args.exact_maxsim, algo=args.algo, **kw)
+        r = run(args.steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         windows.append((t0, t0 + dt))
@@ -722,7 +742,9 @@ def main() -> None:  # noqa: PLR0915
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return r, float(tt.item()) * 1e3 / args.steps
 
-    (ids, sims, counts), e2e_ms = timed_e2e()
+    (ids_s, sims_s, counts_s), e2e_serial_ms = timed_e2e(1)
+    (ids, sims, counts), e2e_ms = timed_e2e(args.inflight) if args.inflight > 1 else ((ids_s, sims_s, counts_s), e2e_serial_ms)
+    assert np.array_equal(ids, ids_s) and np.array_equal(counts, counts_s), "pipelined and serial searches disagree"
     e2e_value = B / (e2e_ms * 1e-3) * norm
     filtered = None
     probe_calls = {"n": 0}
@@ -735,12 +757,12 @@ def main() -> None:  # noqa: PLR0915
 
         type(local).count_at_least = _counting
     if args.filtered:   # both reference branches (_search.py:96-143), same batch, same API
-        _, ms_rare = timed_e2e(metadata_filter={"rare": 1})      # <= 100k matching rows: filter, then rank
-        _, ms_half = timed_e2e(metadata_filter={"half": 1})      # > 100k rows in a > 1M-vector table: rank, then filter
-        filtered = {"filter_first_ms": ms_rare, "rank_then_filter_ms": ms_half, "unfiltered_ms": e2e_ms,
+        _, ms_rare = timed_e2e(1, metadata_filter={"rare": 1})      # <= 100k matching rows: filter, then rank
+        _, ms_half = timed_e2e(1, metadata_filter={"half": 1})      # > 100k rows in a > 1M-vector table: rank, then filter
+        filtered = {"filter_first_ms": ms_rare, "rank_then_filter_ms": ms_half, "unfiltered_ms": e2e_serial_ms,
                     "rank_probe_passes_over_the_corpus": probe_calls["n"], "matching_rows_rare": int(local.filter_chunks({"rare": [1]})[1]),
                     "matching_rows_half": int(local.filter_chunks({"half": [1]})[1]),
-                    "filter_first_vs_unfiltered": ms_rare / e2e_ms, "rank_then_filter_vs_unfiltered": ms_half / e2e_ms}
+                    "filter_first_vs_unfiltered": ms_rare / e2e_serial_ms, "rank_then_filter_vs_unfiltered": ms_half / e2e_serial_ms}
     clocks = sampler.stop(windows)
     clocks["windows"] = "timed device steps + timed e2e steps"
 
@@ -769,7 +791,11 @@ def main() -> None:  # noqa: PLR0915
             "queries_per_sec_raw": qps_raw,
             "e2e": {"value": e2e_value, "unit": "queries/s (10M-chunk equivalent)", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(B * d * 4), "d2h_bytes_per_step": int(B * k * 12 + B * 4 + 4),
-                    "api": "raglite_b200.vector_search_batch (pinned host queries in -> host numpy out, one sync)"},
+                    "api": ("raglite_b200.vector_search_batch_async, %d batches in flight (each: pinned host queries in -> its own stream "
+                            "-> pinned host results out)" % args.inflight) if args.inflight > 1 else
+                           "raglite_b200.vector_search_batch (pinned host queries in -> host numpy out, one sync)",
+                    "batches_in_flight": max(1, args.inflight),
+                    "serial_ms_per_step": e2e_serial_ms, "serial_api": "raglite_b200.vector_search_batch, one call after the other"},
             "gpu_launches": int((stats["launches"] + 1 + (1 if use_adapter else 0)) * args.steps),
             "launches_per_step": {"scan_pipeline": stats["launches"], "merge": 1, "adapter_apply": 1 if use_adapter else 0},
             "roofline": roofline,

@@ -23,6 +23,7 @@ from ._search import (
     search_and_rerank_chunks,
     vector_search,
     vector_search_batch,
+    vector_search_batch_async,
 )
 
 __all__ = [
@@ -49,4 +50,5 @@ __all__ = [
     "update_query_adapter",
     "vector_search",
     "vector_search_batch",
+    "vector_search_batch_async",
 ]

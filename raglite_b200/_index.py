@@ -182,7 +182,8 @@ class CorpusIndex:
         self._meta_inv: dict[tuple[str, Any], np.ndarray] | None = None   # (key, value) -> chunk indices
         self._meta_inv_chunks = 0                      # chunks covered by _meta_inv
         self._filter_cache: dict[Any, tuple[torch.Tensor, int]] = {}      # filter -> (chunk_ok uint8 [C], matching live rows)
-        self._pinned: dict[int, torch.Tensor] = {}     # result staging buffers (pinned host memory) by size
+        self._pinned: dict[Any, torch.Tensor] = {}     # result staging buffers (pinned host memory) by (size, stream)
+        self._slots: list[Any] = []                    # streams + pinned buffers of the asynchronous searches (search_async)
         self.last_params: ScanParams | None = None
         self.last_ws: torch.Tensor | None = None
         with torch.cuda.device(self.device):
@@ -778,38 +779,48 @@ class CorpusIndex:
         return self.chunk_ids[local] if self.chunk_ids is not None else str(int(global_chunk))
 
     # ---- results to the host in one copy ------------------------------------------------------------------
-    def to_host(self, sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor,
-                extra: torch.Tensor | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray, int] | tuple:
-        """One device->host copy (pinned staging buffer) of a merged result plus the OR of the status words,
-        then ONE stream synchronisation -- the only host sync of a search."""
-        B, k = int(sim.shape[0]), int(sim.shape[1])
+    @staticmethod
+    def _pack_result(sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor,
+                     extra: torch.Tensor | None = None) -> torch.Tensor:
+        """[extra int64 [B]] | chunk int64 [B, k] | sim float32 [B, k] | count int32 [B] | OR of the status words."""
         st_any = status.reshape(-1).to(torch.int32)
         st_any = st_any.max().reshape(1) if st_any.numel() else torch.zeros(1, dtype=torch.int32, device=sim.device)
         parts = [chunk.contiguous().view(torch.uint8).reshape(-1), sim.contiguous().view(torch.uint8).reshape(-1),
                  count.to(torch.int32).contiguous().view(torch.uint8).reshape(-1), st_any.view(torch.uint8).reshape(-1)]
         if extra is not None:   # an int64 [B] vector rides along (e.g. the rank-then-filter bound)
             parts.insert(0, extra.to(torch.int64).contiguous().view(torch.uint8).reshape(-1))
-        dev = torch.cat(parts)
-        n = int(dev.numel())
-        host = self._pinned.get(n)
-        if host is None:
-            if len(self._pinned) >= 8:
-                self._pinned.pop(next(iter(self._pinned)))
-            host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-            self._pinned[n] = host
-        host.copy_(dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        raw = host.numpy()
+        return torch.cat(parts)
+
+    @staticmethod
+    def _parse_result(raw: np.ndarray, B: int, k: int, n_extra: int = 0) -> tuple:
         ext = None
-        if extra is not None:
-            ext = raw[: extra.numel() * 8].view(np.int64).copy()
-            raw = raw[extra.numel() * 8:]
+        if n_extra:
+            ext = raw[: n_extra * 8].view(np.int64).copy()
+            raw = raw[n_extra * 8:]
         n8, n4 = B * k * 8, B * k * 4
         ids = raw[:n8].view(np.int64).reshape(B, k).copy()
         sims = raw[n8:n8 + n4].view(np.float32).reshape(B, k).copy()
         counts = raw[n8 + n4:n8 + n4 + B * 4].view(np.int32).copy()
         st = int(raw[n8 + n4 + B * 4:].view(np.int32)[0])
-        return (ids, sims, counts, st) if extra is None else (ids, sims, counts, st, ext)
+        return (ids, sims, counts, st) if ext is None else (ids, sims, counts, st, ext)
+
+    def to_host(self, sim: torch.Tensor, chunk: torch.Tensor, count: torch.Tensor, status: torch.Tensor,
+                extra: torch.Tensor | None = None) -> tuple[np.ndarray, np.ndarray, np.ndarray, int] | tuple:
+        """One device->host copy (pinned staging buffer) of a merged result plus the OR of the status words,
+        then ONE stream synchronisation -- the only host sync of a search."""
+        B, k = int(sim.shape[0]), int(sim.shape[1])
+        dev = self._pack_result(sim, chunk, count, status, extra)
+        n = int(dev.numel())
+        key = (n, _stream())      # one staging buffer per (size, stream): concurrent searches never share one
+        host = self._pinned.get(key)
+        if host is None:
+            if len(self._pinned) >= 16:
+                self._pinned.pop(next(iter(self._pinned)))
+            host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            self._pinned[key] = host
+        host.copy_(dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._parse_result(host.numpy(), B, k, 0 if extra is None else int(extra.numel()))
 
 
 def next_overflow_attempt(local: "CorpusIndex", attempt: int, cap: int, base_flags: int) -> tuple[int, int]:
@@ -860,6 +871,89 @@ def search_to_host(  # noqa: PLR0913
                 return ids, sims, counts
             cap, flags = next_overflow_attempt(local, attempt + 1, cap, 0)
     raise _lib.RagliteB200Error("candidate lists still overflow with a list as large as the shard")
+
+
+class _SearchSlot:
+    """A CUDA stream with its own pinned result buffer: one search in flight."""
+
+    def __init__(self, device: Any):
+        self.stream = torch.cuda.Stream(device=device)
+        self.host: torch.Tensor | None = None
+        self.busy = False
+
+
+class PendingSearch:
+    """A search that has been enqueued on its own stream (queries up, kernels, results down to a private pinned
+    buffer) but not waited for.  ``result()`` waits for THAT stream only; a candidate-list overflow (rare: adversarial
+    row order, masses of near-ties) is then resolved by re-running the search synchronously on the same stream."""
+
+    def __init__(self, index: Any, Q: torch.Tensor, kw: dict[str, Any], slot: _SearchSlot | None, event: Any, B: int, k: int,
+                 ready: tuple | None = None):
+        self._index, self._Q, self._kw, self._slot, self._event, self._B, self._k, self._ready = index, Q, kw, slot, event, B, k, ready
+
+    def done(self) -> bool:
+        return self._ready is not None or bool(self._event.query())
+
+    def result(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        if self._ready is None:
+            slot = self._slot
+            self._event.synchronize()
+            ids, sims, counts, st = CorpusIndex._parse_result(slot.host.numpy(), self._B, self._k)
+            if st & RL_STATUS_CAND_OVERFLOW:
+                with torch.cuda.stream(slot.stream):
+                    ids, sims, counts = search_to_host(self._index, self._Q, **self._kw)
+            slot.busy = False
+            self._ready = (ids, sims, counts)
+            self._Q = None
+        return self._ready
+
+
+def search_async(  # noqa: PLR0913
+    index: Any, queries: Any, *, k: int, num_hits: int, metric: str, algo: str = "auto", chunk_ok: torch.Tensor | None = None,
+    rank_first_limit: int | None = None, prepare: Any | None = None, max_in_flight: int = 8,
+) -> PendingSearch:
+    """``search_to_host`` without the wait: picks a free (stream, pinned buffer) slot of the index, and on that stream
+    uploads the queries, runs ``prepare`` (e.g. the query adapter), enqueues scan -> [all-gather] -> merge and the
+    device->host copy of the result.  Several calls overlap on the GPU -- the tail of one batch's scan with the
+    sampling pass and selection of the next, the copies and the host-side launch work with everything -- which is
+    how a server keeps the device busy.  The calling thread issues all launches (and, on a sharded index, all
+    collectives) in program order, so every rank sees the same order.  Searches that may need a second corpus pass
+    on the host's decision (the rank-then-filter branch) run synchronously on the slot's stream."""
+    local: CorpusIndex = getattr(index, "local", index)
+    with local._lock:
+        slot = next((sl for sl in local._slots if not sl.busy), None)
+        if slot is None:
+            if len(local._slots) >= max_in_flight:
+                raise RuntimeError(f"{max_in_flight} searches are already in flight on this index; collect a result() first")
+            slot = _SearchSlot(local.device)
+            local._slots.append(slot)
+        slot.busy = True
+    kw = dict(k=k, num_hits=num_hits, metric=metric, algo=algo, chunk_ok=chunk_ok, rank_first_limit=rank_first_limit)
+    try:
+        slot.stream.wait_stream(torch.cuda.current_stream(local.device))   # inputs produced on the caller's stream
+        with torch.cuda.device(local.device), torch.cuda.stream(slot.stream):
+            Q = torch.as_tensor(queries).to(device=local.device, dtype=torch.float32, non_blocking=True).contiguous()
+            if prepare is not None:
+                Q = prepare(Q)
+            B = int(Q.shape[0])
+            if rank_first_limit is not None:
+                out = search_to_host(index, Q, **kw)
+                slot.busy = False
+                return PendingSearch(index, Q, kw, None, None, B, k, ready=out)
+            with local._lock:
+                mask = local.row_mask(chunk_ok)
+                sim, chunk, count, status = index.search_pipeline(Q, k=k, num_hits=num_hits, metric=metric, algo=algo,
+                                                                  row_allowed=mask, mask_has_tombstones=True)
+                dev = local._pack_result(sim, chunk, count, status)
+            if slot.host is None or slot.host.numel() != dev.numel():
+                slot.host = torch.empty(int(dev.numel()), dtype=torch.uint8, pin_memory=True)
+            slot.host.copy_(dev, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(slot.stream)
+        return PendingSearch(index, Q, kw, slot, event, B, k)
+    except Exception:
+        slot.busy = False
+        raise
 
 
 def merge_hits(  # noqa: PLR0913

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ._config import RAGLiteConfig
-from ._index import Chunk, CorpusIndex, get_index, search_to_host
+from ._index import Chunk, CorpusIndex, PendingSearch, get_index, search_async, search_to_host
 from ._typing import ChunkId, FloatVector, MetadataFilter
 
 REFERENCE_CHUNK_MAX_SIZE = 2048  # RAGLiteConfig.chunk_max_size class default (_config.py:67)
@@ -49,6 +49,48 @@ def _filter_on_device(index: Any, metadata_filter: dict[str, list[Any]] | None) 
     return local.filter_chunks(metadata_filter)
 
 
+def _plan_search(  # noqa: PLR0913
+    queries: Any, *, num_results: int, oversample: int, metadata_filter: MetadataFilter | None, config: RAGLiteConfig | None,
+    index: Any | None, exact_maxsim: bool, queries_are_fp16: bool,
+) -> tuple[Any, torch.Tensor, tuple | None, dict[str, Any], Any]:
+    """Argument handling shared by the synchronous and the asynchronous batched search: returns
+    ``(index, Q (as given, not yet on the device), empty result or None, search kwargs, prepare(Q_device))``."""
+    config = config or RAGLiteConfig()
+    index = index if index is not None else get_index(config)
+    if index is None:
+        raise ValueError(f"No index registered for db_url={config.db_url!r}; use raglite_b200.register_index")
+    local: CorpusIndex = getattr(index, "local", index)
+    Q = torch.as_tensor(queries)
+    queries_are_fp16 = queries_are_fp16 or Q.dtype == torch.float16
+    if Q.ndim != 2:
+        raise ValueError("queries must be [B, d]")
+    k = int(num_results)
+    B = int(Q.shape[0])
+    sharded = hasattr(index, "group")
+    empty = (np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32))
+    if local.n_live_chunks == 0 and not sharded:
+        return index, Q, empty, {}, None
+    num_hits = 0 if exact_maxsim else num_hits_rule(k, oversample, config.chunk_max_size)
+    if not exact_maxsim and num_hits == 0:  # round(oversample * size / 2048) == 0 -> LIMIT 0
+        return index, Q, empty, {}, None
+    prepare = None
+    if config.vector_search_query_adapter and local.query_adapter is not None:
+        def prepare(Qd: torch.Tensor) -> torch.Tensor:  # (A @ q).astype(q.dtype), _search.py:58-62
+            return local.apply_adapter(Qd, round_fp16=queries_are_fp16)
+    chunk_ok, n_match = _filter_on_device(index, _adapt_metadata(metadata_filter))
+    metric = config.vector_search_distance_metric
+    # Which metadata branch the reference would take (_search.py:96-143): many matching rows in a corpus
+    # of more than 1M vectors -> only filtered hits among the 1M nearest vectors overall count.
+    rank_first_limit = None
+    if chunk_ok is not None and num_hits > 0:
+        totals = [n_match, local.n_live_rows]
+        if sharded:
+            totals = index.sum_over_shards(torch.tensor(totals, dtype=torch.int64, device=local.device)).tolist()
+        if totals[0] > FILTER_FIRST_MAX_ROWS and totals[1] > RANK_FIRST_LIMIT:
+            rank_first_limit = RANK_FIRST_LIMIT
+    return index, Q, None, dict(k=k, num_hits=num_hits, metric=metric, chunk_ok=chunk_ok, rank_first_limit=rank_first_limit), prepare
+
+
 def vector_search_batch(  # noqa: PLR0913
     queries: np.ndarray | torch.Tensor,
     *,
@@ -68,39 +110,42 @@ def vector_search_batch(  # noqa: PLR0913
     top-``num_hits``-vectors semantics.  Host work per call is O(B): the query upload, kernel launches,
     one pinned device->host copy of the results and one stream synchronisation.
     """
-    config = config or RAGLiteConfig()
-    index = index if index is not None else get_index(config)
-    if index is None:
-        raise ValueError(f"No index registered for db_url={config.db_url!r}; use raglite_b200.register_index")
+    index, Q, empty, kw, prepare = _plan_search(queries, num_results=num_results, oversample=oversample,
+                                                metadata_filter=metadata_filter, config=config, index=index,
+                                                exact_maxsim=exact_maxsim, queries_are_fp16=queries_are_fp16)
+    if empty is not None:
+        return empty
     local: CorpusIndex = getattr(index, "local", index)
-    Q = torch.as_tensor(queries)
-    queries_are_fp16 = queries_are_fp16 or Q.dtype == torch.float16
     Q = Q.to(device=local.device, dtype=torch.float32, non_blocking=True).contiguous()
-    if Q.ndim != 2:
-        raise ValueError("queries must be [B, d]")
-    k = int(num_results)
-    B = int(Q.shape[0])
-    sharded = hasattr(index, "group")
-    if local.n_live_chunks == 0 and not sharded:
-        return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
-    if config.vector_search_query_adapter and local.query_adapter is not None:
-        Q = local.apply_adapter(Q, round_fp16=queries_are_fp16)
-    num_hits = 0 if exact_maxsim else num_hits_rule(k, oversample, config.chunk_max_size)
-    if not exact_maxsim and num_hits == 0:  # round(oversample * size / 2048) == 0 -> LIMIT 0
-        return np.full((B, k), -1, np.int64), np.full((B, k), -np.inf, np.float32), np.zeros(B, np.int32)
-    chunk_ok, n_match = _filter_on_device(index, _adapt_metadata(metadata_filter))
-    metric = config.vector_search_distance_metric
-    # Which metadata branch the reference would take (_search.py:96-143): many matching rows in a corpus
-    # of more than 1M vectors -> only filtered hits among the 1M nearest vectors overall count.
-    rank_first_limit = None
-    if chunk_ok is not None and num_hits > 0:
-        totals = [n_match, local.n_live_rows]
-        if sharded:
-            totals = index.sum_over_shards(torch.tensor(totals, dtype=torch.int64, device=local.device)).tolist()
-        if totals[0] > FILTER_FIRST_MAX_ROWS and totals[1] > RANK_FIRST_LIMIT:
-            rank_first_limit = RANK_FIRST_LIMIT
-    return search_to_host(index, Q, k=k, num_hits=num_hits, metric=metric, algo=algo, chunk_ok=chunk_ok,
-                          rank_first_limit=rank_first_limit)
+    if prepare is not None:
+        Q = prepare(Q)
+    return search_to_host(index, Q, algo=algo, **kw)
+
+
+def vector_search_batch_async(  # noqa: PLR0913
+    queries: np.ndarray | torch.Tensor,
+    *,
+    num_results: int = 3,
+    oversample: int = 4,
+    metadata_filter: MetadataFilter | None = None,
+    config: RAGLiteConfig | None = None,
+    index: Any | None = None,
+    exact_maxsim: bool = False,
+    algo: str = "auto",
+    queries_are_fp16: bool = False,
+) -> PendingSearch:
+    """``vector_search_batch`` that returns at once with a :class:`PendingSearch`; ``.result()`` gives the same three
+    host arrays.  Each call runs on a stream of its own (query upload, kernels, result download into a private
+    pinned buffer), so a caller that keeps two or three batches in flight -- what a retrieval server does -- never
+    leaves the GPU idle between batches: the host-side work of batch i + 1 and the copies of batch i hide under the
+    corpus scan, and the small kernels at either end of a search fill the scan's tail.  (The reference reaches the same
+    concurrency with its thread pool, _rag.py:317; here one thread suffices.)"""
+    index, Q, empty, kw, prepare = _plan_search(queries, num_results=num_results, oversample=oversample,
+                                                metadata_filter=metadata_filter, config=config, index=index,
+                                                exact_maxsim=exact_maxsim, queries_are_fp16=queries_are_fp16)
+    if empty is not None:
+        return PendingSearch(index, Q, {}, None, None, int(Q.shape[0]), int(num_results), ready=empty)
+    return search_async(index, Q, algo=algo, prepare=prepare, **kw)
 
 
 def vector_search(

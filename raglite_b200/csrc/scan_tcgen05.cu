@@ -32,6 +32,9 @@ namespace {
 
 using namespace tc;
 
+#ifndef RL_EPI_SIGN
+#define RL_EPI_SIGN 1   // emit-mode epilogue: sign collector (FFMA + funnel shift) instead of FMUL + FSETP + SEL
+#endif
 constexpr int kTileM = 128;           // corpus rows per tile (UMMA M)
 constexpr int kSliceK = 64;           // fp16 elements per K slice = one 128-byte swizzle row
 constexpr int kMaxQ = 256;            // queries per pass (UMMA N <= 256)
@@ -64,6 +67,7 @@ struct TcArgs {
   int stages;
   int tmem_cols;          // allocated TMEM columns (power of two >= 2 * buf_cols)
   int buf_cols;           // columns per accumulator buffer (nq rounded up to 32)
+  int pf_pairs;           // fast fp32 loader: L2 prefetch distance in pairs of K-slice items (0: no prefetch)
 };
 
 // Global power-of-two row scale for the dot / l2 metrics (keeps |x| <= 1 in fp16).
@@ -215,6 +219,9 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
                            (EF16 || (t.row_stats[2] > 0.f && t.row_stats[2] <= 2.f && t.row_stats[1] <= 1024.f &&
                                      t.row_stats[3] == 0.f));   // (the host only allows fp16 storage when this holds)
 
+  // fp32 loader fast path (uniform): whole K slices in pairs, one query group per CTA, no per-row scale in the loader
+  const bool fast_f32 = !EF16 && G0 == 1 && a.d % kSliceK == 0 && (t.n_ks & 1) == 0 && a.ld * 64 < (int64_t(1) << 32) &&
+                        (METRIC != RL_METRIC_COSINE || cos_noscale);
   if (EF16 && warp >= kFirstLoaderWarp) {
     // ===== corpus loaders, fp16 storage: HBM -> registers -> swizzled smem, no conversion =====
     // A K slice of a row is 128 bytes = 8 chunks of 16 bytes; thread lt owns chunk lt & 7 of rows
@@ -313,6 +320,118 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       if (item + 1 < total_items) process(ring[1]);
       if (item + 2 < total_items) process(ring[2]);
       if (item + 3 < total_items) process(ring[3]);
+    }
+  } else if (warp >= kFirstLoaderWarp && fast_f32) {
+    // ===== corpus loaders, fp32 storage, FAST PATH (d % 128 == 0, one query group per CTA, no per-row scale) =====
+    // Same data movement as the generic loader below -- HBM fp32 -> registers (two K-slice items = 64 KB per SM in
+    // flight) -> cvt.rn.f16x2 -> 128B-swizzled smem tile, L2 prefetch kPrefetchItems ahead -- with the bookkeeping
+    // cut down.  ncu's source view of the generic loop showed ~155 SASS instructions per item and warp (three
+    // cursors with 64-bit row pointers rebuilt per item, constants re-read from the parameter bank, the swizzle offset
+    // rematerialised from %tid), and the loader warps, not memory, setting the pace at the power-capped SM clock:
+    // 28 % "wait" + 15 % "selected" stall samples, a ~1000-cycle dependent chain per 1100-cycle item.  Here an
+    // iteration handles the PAIR of items (ks, ks + 1): one cursor step, seven row pointers (32-bit pitch, one
+    // IMAD.WIDE each) shared by both items through a +256 B immediate, smem / barrier addresses kept incrementally.
+    const int lt = threadIdx.x - kFirstLoaderWarp * 32;  // 0..255
+    const int c4 = lt & 15;                              // float4 column within the 64-wide K slice
+    const int r0 = lt >> 4;                              // rows r0 + 16 i, i = 0..7
+    const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
+    const bool mul = gscale != 1.f;
+    uint32_t n_ks = (uint32_t)t.n_ks, n_stages = (uint32_t)t.stages;
+    uint32_t pitch16 = (uint32_t)(a.ld * 16 * (int64_t)sizeof(float));   // bytes between this thread's consecutive rows
+    uint32_t sw_off = (uint32_t)r0 * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r0 & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+    // opaque moves: keep these in registers instead of re-deriving them from %tid / the parameter bank per item
+    asm volatile("" : "+r"(n_ks), "+r"(n_stages), "+r"(pitch16), "+r"(sw_off));
+    const int64_t total_items = my_tiles * (int64_t)n_ks;
+
+    struct Cursor { int64_t tile; uint32_t ks; int rows; const unsigned char* ptr; };
+    // Load cursor: this thread's row r0 / column c4 of the NEXT pair of items to load.
+    Cursor ld{0, 0u, 0, nullptr};
+    auto ld_set_tile = [&]() {
+      ld.rows = 0;
+      if (ld.tile < my_tiles) {
+        const int64_t ord = ord_of(ld.tile);
+        if (ord < a.n_mode_blocks) {
+          const int64_t blk = mode_block_index(a, ord);
+          const int64_t rem = a.n_rows - blk * kTileM;
+          ld.rows = rem < kTileM ? (int)rem : kTileM;
+          ld.ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + r0) * a.ld + c4 * 4);
+        }
+      }
+    };
+    // Prefetch cursor (L2 only): thread lt covers row lt / 2, 128-byte half lt % 2 of a 256-byte slice.
+    Cursor pf{0, 0u, 0, nullptr};
+    auto pf_set_tile = [&]() {
+      pf.rows = 0;
+      if (pg == 0 && t.pf_pairs > 0 && pf.tile < my_tiles) {
+        const int64_t ord = ord_of(pf.tile);
+        if (ord < a.n_mode_blocks) {
+          const int64_t blk = mode_block_index(a, ord);
+          const int64_t rem = a.n_rows - blk * kTileM;
+          pf.rows = rem < kTileM ? (int)rem : kTileM;
+          pf.ptr = reinterpret_cast<const unsigned char*>(a.E + (size_t)(blk * kTileM + (lt >> 1)) * a.ld + (lt & 1) * 32);
+          if (METRIC == RL_METRIC_COSINE && lt < 4 && lt * 32 < pf.rows) prefetch_l2(a.inv_norm + blk * kTileM + lt * 32);
+        }
+      }
+    };
+    auto pf_pair = [&]() {
+      if ((lt >> 1) < pf.rows) { prefetch_l2(pf.ptr); prefetch_l2(pf.ptr + 256); }
+      pf.ptr += 512;
+      pf.ks += 2;
+      if (pf.ks == n_ks) { pf.ks = 0; ++pf.tile; pf_set_tile(); }
+    };
+    float4 ringA[8], ringB[8];
+    auto issue = [&](float4 (&buf)[8], int rows, const unsigned char* base) {   // base: row r0 of the item
+      if (rows == kTileM) {   // full tile: no per-row predicates
+#pragma unroll
+        for (int i = 0; i < 8; ++i) buf[i] = ldg_stream(reinterpret_cast<const float*>(base + (size_t)((uint32_t)i * pitch16)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (r0 + 16 * i < rows) buf[i] = ldg_stream(reinterpret_cast<const float*>(base + (size_t)((uint32_t)i * pitch16)));
+          else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    // Store side: shared-memory addresses of the current stage, kept incrementally.
+    uint32_t stage = 0, phase = 0;
+    unsigned char* a_dst = s.stage_base + sw_off;
+    auto store = [&](const float4 (&buf)[8]) {
+      mbar_wait(&s.empty[stage], phase ^ 1u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 v = buf[i];
+        if (mul) { v.x *= gscale; v.y *= gscale; v.z *= gscale; v.w *= gscale; }
+        const __half2 h01 = __floats2half2_rn(v.x, v.y);
+        const __half2 h23 = __floats2half2_rn(v.z, v.w);
+        uint2 packed;
+        packed.x = *reinterpret_cast<const uint32_t*>(&h01);
+        packed.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(a_dst + i * 16 * 128) = packed;
+      }
+      // (no proxy fence here, see the generic loader: the MMA thread fences after acquiring the barrier)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.full[stage]);
+      a_dst += sbytes;
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; a_dst = s.stage_base + sw_off; }
+    };
+
+    ld_set_tile();
+    pf_set_tile();
+    for (int i = 0; i < t.pf_pairs + 1; ++i) pf_pair();   // the load cursor starts one pair ahead of the stores
+    issue(ringA, ld.rows, ld.ptr);
+    issue(ringB, ld.rows, ld.ptr + 256);
+    for (int64_t item = 0; item < total_items; item += 2) {
+      // advance the load cursor to the next pair (possibly the first pair of the next tile)
+      ld.ptr += 512;
+      ld.ks += 2;
+      if (ld.ks == n_ks) { ld.ks = 0; ++ld.tile; ld_set_tile(); }
+      const int rows = ld.rows;
+      const unsigned char* base = ld.ptr;
+      store(ringA);
+      issue(ringA, rows, base);
+      store(ringB);
+      issue(ringB, rows, base + 256);
+      pf_pair();
     }
   } else if (warp >= kFirstLoaderWarp) {
     // ===== corpus loaders: HBM fp32 -> registers -> fp16 -> swizzled smem (UMMA A operand) =====
@@ -576,6 +695,24 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             }
           }
         } else {
+          // Two instructions per accumulator: the sign of  acc * scale - thr  (one FFMA; dot / l2: FFMA + FADD) is
+          // shifted into a bit collector with one funnel shift -- element j ends up at bit 31 - j, set when the
+          // key is BELOW its threshold.  (Was FMUL + FSETP + SEL + an occasional IADD3: 3.5 per accumulator, a
+          // quarter of the SM's issued instructions.)  For cosine the FFMA rounds once, so a key whose rounded
+          // product equals thr while the exact product lies below it no longer counts as a hit; thr sits 2 eps
+          // (~1e-3) under anything the selection needs, a rounding step is 6e-8.
+#if RL_EPI_SIGN
+          uint32_t below = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float acc = __uint_as_float(v[j]);
+            float tkey;
+            if (METRIC != RL_METRIC_COSINE) tkey = fmaf(acc, s.cs[q0 + c0 + j], bias) - s.thr[q0 + c0 + j];
+            else tkey = fmaf(acc, lane_scale, -s.thr[q0 + c0 + j]);
+            below = __funnelshift_l(__float_as_uint(tkey), below, 1);
+          }
+          uint32_t mask = __brev(~below);   // bit j set <=> key j at or above its threshold
+#else
           uint32_t mask = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -584,6 +721,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
             else key *= lane_scale;
             if (key >= s.thr[q0 + c0 + j]) mask |= 1u << j;
           }
+#endif
           if (masked_alive) {   // (only with RL_FLAG_COUNT_UNFILTERED on a filtered scan)
             uint32_t extra = mask;
             while (extra != 0) {
@@ -1244,6 +1382,8 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.nq_last = (last_b + 15) / 16 * 16;
     t.nq = ng > 1 ? kMaxQ : t.nq_last;                     // a full group (the only group when ng == 1)
     t.n_ks = n_ks;
+    static const int pf_pairs_env = []() { const char* e = getenv("RL_TC_PF_PAIRS"); return e ? atoi(e) : kPrefetchItems / 2; }();
+    t.pf_pairs = pf_pairs_env < 0 ? 0 : (pf_pairs_env > 16 ? 16 : pf_pairs_env);
     t.buf_cols = (t.nq + 31) / 32 * 32;
     int cols = 32;
     while (cols < 2 * t.buf_cols) cols *= 2;

@@ -54,6 +54,14 @@ def _worker(rank: int, world: int, port: int, tmp: str) -> None:
     both = [None] * world
     dist.all_gather_object(both, ids.tolist())
     assert both[0] == both[1], "every rank must hold the same merged result"
+    # 1b) three searches in flight on their own streams (one thread: launches and collectives in program order on
+    # every rank) return what the serial calls return
+    parts = [Q[:8], Q[8:16], Q[16:]]
+    want = [rl.vector_search_batch(p, num_results=10, config=cfg, index=index) for p in parts]
+    pend = [rl.vector_search_batch_async(torch.from_numpy(p).pin_memory(), num_results=10, config=cfg, index=index) for p in parts]
+    for w_, p_ in zip(want, pend, strict=True):
+        g_ = p_.result()
+        assert np.array_equal(g_[0], w_[0]) and np.array_equal(g_[1], w_[1]) and np.array_equal(g_[2], w_[2])
     # 2) candidate overflow on the shards: the status words travel with the hits, all ranks retry together
     Qd = torch.from_numpy(Q).cuda()
     sim, chunk, count = index.search_device(Qd, k=10, num_hits=40, sample_stride=32, checked=True)

@@ -615,3 +615,46 @@ def test_merge_of_more_hits_than_the_window(rl):
         n = int(out_count[b])
         assert n == len(keep)
         assert np.array_equal(out_chunk[b, :n], c[keep]) and np.array_equal(out_sim[b, :n], s[keep])
+
+
+def test_async_searches_in_flight_match_the_serial_call(rl):
+    """vector_search_batch_async: several batches in flight on their own streams (uploads, kernels, pinned downloads
+    overlapping) return exactly what the serial call returns, in any collection order, with and without the query
+    adapter and a metadata filter; a slot is reusable once its result has been collected."""
+    import torch
+
+    E, off = make_corpus(6000, (1, 10), 128, seed=31)
+    n_chunks = len(off) - 1
+    idx = rl.CorpusIndex(E, off, chunk_metadata=[{"even": int(c % 2 == 0)} for c in range(n_chunks)])
+    idx.set_query_adapter(random_orthogonal(128, seed=5))
+    batches = [make_queries(E, 24, seed=100 + i) for i in range(7)]
+    for adapter, flt in ((False, None), (True, None), (True, {"even": 1})):
+        cfg = rl.RAGLiteConfig(reranker=None, vector_search_query_adapter=adapter)
+        kw = dict(num_results=10, config=cfg, index=idx, metadata_filter=flt)
+        want = [rl.vector_search_batch(Q, **kw) for Q in batches]
+        pinned = [torch.from_numpy(Q).pin_memory() for Q in batches]
+        pend = [rl.vector_search_batch_async(Q, **kw) for Q in pinned[:3]]      # three in flight
+        got = {2: pend[2].result(), 0: pend[0].result()}                         # out of order
+        pend += [rl.vector_search_batch_async(Q, **kw) for Q in pinned[3:5]]    # reuses the two freed slots
+        for i in (1, 3, 4):
+            got[i] = pend[i].result()
+        pend += [rl.vector_search_batch_async(Q, **kw) for Q in pinned[5:]]
+        for i in (5, 6):
+            got[i] = pend[i].result()
+        assert pend[0].done() and pend[0].result() is got[0]
+        for i, (ids, sims, counts) in enumerate(want):
+            assert np.array_equal(got[i][0], ids) and np.array_equal(got[i][2], counts), (adapter, flt, i)
+            assert np.array_equal(got[i][1], sims), (adapter, flt, i)
+        if flt is not None:
+            assert all(int(c) % 2 == 0 for c in got[0][0][got[0][0] >= 0])
+    assert len(idx._slots) == 3 and not any(sl.busy for sl in idx._slots)
+    from raglite_b200._index import search_async
+
+    held = [search_async(idx, pinned[0], k=10, num_hits=40, metric="cosine", max_in_flight=3) for _ in range(3)]
+    with pytest.raises(RuntimeError, match="in flight"):   # a fourth search needs a result() first
+        search_async(idx, pinned[0], k=10, num_hits=40, metric="cosine", max_in_flight=3)
+    first = held[0].result()
+    again = search_async(idx, pinned[0], k=10, num_hits=40, metric="cosine", max_in_flight=3).result()
+    assert np.array_equal(first[0], again[0])
+    for h in held[1:]:
+        assert np.array_equal(h.result()[0], first[0])
