@@ -18,9 +18,11 @@
 //     keys, flushed in bulk (one global atomic per touched query / bin), and the global histogram is
 //     read back to tighten the thresholds while the scan is running (online refinement).
 // All hand-offs are mbarrier based (full/empty per smem stage, full/empty per TMEM buffer).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "scan_tcgen05.cuh"
@@ -68,7 +70,19 @@ struct TcArgs {
   int tmem_cols;          // allocated TMEM columns (power of two >= 2 * buf_cols)
   int buf_cols;           // columns per accumulator buffer (nq rounded up to 32)
   int pf_pairs;           // fast fp32 loader: L2 prefetch distance in pairs of K-slice items (0: no prefetch)
+  int tma_rows;           // fp16 storage: 1 = corpus tiles come through the tensor map (no loader warps)
 };
+
+// TMA tensor-map tile load (2-D, 128B swizzle: the UMMA K-major SW128 layout) and its L2-only prefetch.
+__device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 
 // Global power-of-two row scale for the dot / l2 metrics (keeps |x| <= 1 in fp16).
 __device__ __forceinline__ float pow2_scale(float max_abs) {
@@ -109,7 +123,7 @@ __host__ __device__ inline uint32_t tail_bytes(int n_groups) {
 // EF16: the corpus is stored as fp16 (lossless for RAGLite data, whose embeddings are fp16-rounded,
 // reference _embed.py:140): rows are copied into the swizzled tile without conversion, half the HBM bytes.
 template <int METRIC, bool PAIR, bool EF16>
-__global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
+__global__ void __maxnreg__(128) scan_tcgen05_kernel(const __grid_constant__ CUtensorMap tmE, const TcArgs t) {
   extern __shared__ unsigned char smem_dyn[];
   // Group-parallel mode (B > 256, the default): the CTAs of a "lane" -- par_groups consecutive CTAs -- walk the
   // SAME corpus tiles at the same time, one 256-query group each.  The first of them pulls a tile in from
@@ -183,7 +197,8 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < t.stages; ++i) {
       // 8 loader warps + the query producer (expect_tx) [+ the peer CTA's relay in the leader]
-      mbar_init(&s.full[i], kNumLoaderWarps + 1 + ((PAIR && rank == 0) ? 1 : 0));
+      // loader warps (none when the tensor map brings the rows) + the producer (expect_tx) [+ the peer's relay]
+      mbar_init(&s.full[i], ((EF16 && t.tma_rows) ? 0 : kNumLoaderWarps) + 1 + ((PAIR && rank == 0) ? 1 : 0));
       mbar_init(&s.empty[i], 1);                   // one tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
@@ -222,16 +237,18 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
   // fp32 loader fast path (uniform): whole K slices in pairs, one query group per CTA, no per-row scale in the loader
   const bool fast_f32 = !EF16 && G0 == 1 && a.d % kSliceK == 0 && (t.n_ks & 1) == 0 && a.ld * 64 < (int64_t(1) << 32) &&
                         (METRIC != RL_METRIC_COSINE || cos_noscale);
-  if (EF16 && warp >= kFirstLoaderWarp) {
+  if (EF16 && t.tma_rows && warp >= kFirstLoaderWarp) {
+    // fp16 storage through the tensor map: the producer thread issues one cp.async.bulk.tensor per K slice and the
+    // TMA engine writes the 128B-swizzled tile itself -- these eight warps have nothing to do.
+  } else if (EF16 && warp >= kFirstLoaderWarp) {
     // ===== corpus loaders, fp16 storage: HBM -> registers -> swizzled smem, no conversion =====
     // A K slice of a row is 128 bytes = 8 chunks of 16 bytes; thread lt owns chunk lt & 7 of rows
     // (lt >> 3) + 32 i.  Four items (4 x 16 KB per SM) stay in flight in registers.
     const int lt = threadIdx.x - kFirstLoaderWarp * 32;
     const int j = lt & 7, r0 = lt >> 3;
     const __half* Eh = reinterpret_cast<const __half*>(a.E);
-    const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
-    const __half2 gs2 = __float2half2_rn(gscale);   // exact power of two (dot / l2 only)
-    const bool scale = gscale != 1.f;
+    // (fp16-stored rows are used as they are: no global power-of-two scale -- it only guards the fp32 -> fp16
+    // conversion against overflow -- and the query scale is built without it, see query_image_kernel)
     const int64_t total_items = v_tiles * t.n_ks;
     const size_t pitch32_bytes = (size_t)a.ld * 32 * sizeof(__half);
     const size_t slice_bytes = kSliceK * sizeof(__half);
@@ -297,13 +314,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       unsigned char* A = s.stage_base + (size_t)stage * sbytes + sw_off;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint4 v = buf[i];
-        if (scale) {
-          __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) h[e] = __hmul2(h[e], gs2);
-        }
-        *reinterpret_cast<uint4*>(A + i * 32 * 128) = v;
+        *reinterpret_cast<uint4*>(A + i * 32 * 128) = buf[i];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.full[stage]);
@@ -587,16 +598,35 @@ __global__ void __maxnreg__(128) scan_tcgen05_kernel(const TcArgs t) {
       const int64_t total_items = v_tiles * t.n_ks;
       int ks = 0, stage = 0, g = 0;
       uint32_t phase = 0;
+      // fp16 storage, tensor-map mode: this thread also brings the corpus tile -- row0 of the current tile (-1: this
+      // CTA has no block for the tile, nothing is loaded and the epilogue ignores the accumulator) and of the
+      // next one, whose slices are prefetched into L2 one tile (n_ks slices = 256 KB per SM at d = 1024) ahead.
+      const bool tma_rows = EF16 && t.tma_rows;
+      int64_t vt = 0;
+      int row0 = -1, row0_next = -1;
+      auto tile_row0 = [&](int64_t v) -> int {
+        if (v >= v_tiles) return -1;
+        const int64_t ord = ord_of(v / G0);
+        return ord < a.n_mode_blocks ? (int)(mode_block_index(a, ord) * kTileM) : -1;
+      };
+      if (tma_rows) { row0 = tile_row0(0); row0_next = tile_row0(1); }
       for (int64_t item = 0; item < total_items; ++item) {
         const uint32_t slice_bytes_q = (uint32_t)(g == G0 - 1 ? nqL : nqF) * 128u;   // one K slice of the group's queries
         const uint32_t qbytes = PAIR ? slice_bytes_q / 2 : slice_bytes_q;                    // PAIR: this CTA's half of them
         const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(qimg_g) + (size_t)g * group_bytes +
                                     (PAIR ? (size_t)rank * qbytes : 0);
         mbar_wait(&s.empty[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&s.full[stage], qbytes);
+        const bool load_a = tma_rows && row0 >= 0;
+        mbar_arrive_expect_tx(&s.full[stage], qbytes + (load_a ? (uint32_t)kABytes : 0u));
+        if (load_a) tma_load_tile(s.stage_base + (size_t)stage * sbytes, &tmE, ks * kSliceK, row0, &s.full[stage]);
         bulk_g2s(s.stage_base + (size_t)stage * sbytes + kABytes, qsrc + (size_t)ks * slice_bytes_q, qbytes,
                  &s.full[stage]);
-        if (++ks == t.n_ks) { ks = 0; if (++g == G0) g = 0; }
+        if (tma_rows && row0_next >= 0 && pg == 0 && g == 0) tma_prefetch_tile(&tmE, ks * kSliceK, row0_next);
+        if (++ks == t.n_ks) {
+          ks = 0;
+          if (++g == G0) g = 0;
+          if (tma_rows) { ++vt; row0 = row0_next; row0_next = tile_row0(vt + 1); }
+        }
         if (++stage == t.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -966,7 +996,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_dual_kernel(const TcArgs t) {
   if (warp >= kDualFirstLoader) {
     const int lt = threadIdx.x - kDualFirstLoader * 32;  // 0..255
     const float gscale = (METRIC == RL_METRIC_COSINE) ? 1.f : pow2_scale(t.row_stats[1]);
-    const bool scale = gscale != 1.f;
+    const bool scale = !EF16 && gscale != 1.f;   // fp16-stored rows are used unscaled
     // Per-thread geometry.  fp32 storage: float4 column c4 of rows r0 + 16 i (i < 8); fp16: 16-byte chunk j of
     // rows r0 + 32 i (i < 4).  Both move 16 KB (one tile's K slice) per item.
     const int c4 = lt & 15, r0f = lt >> 4;
@@ -1279,7 +1309,7 @@ __global__ void __maxnreg__(128) scan_tcgen05_dual_kernel(const TcArgs t) {
 __global__ void __launch_bounds__(128) query_image_kernel(const float* __restrict__ Q, int B, int d, int metric,
                                                           const float* __restrict__ q_inv_norm,
                                                           const float* __restrict__ row_stats, float* __restrict__ q_scale,
-                                                          __half* __restrict__ qimg, int n_ks) {
+                                                          __half* __restrict__ qimg, int n_ks, int rows_scaled) {
   __shared__ float red[4];
   const int b = blockIdx.x;
   const int group = b / kMaxQ, n = b % kMaxQ;
@@ -1298,7 +1328,8 @@ __global__ void __launch_bounds__(128) query_image_kernel(const float* __restric
     __syncthreads();
     m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
     scale = pow2_scale(m);
-    const float rs_e = pow2_scale(row_stats[1]);
+    // the loaders of an fp32 corpus multiply the rows by a global power of two (dot / l2); fp16-stored rows stay as they are
+    const float rs_e = rows_scaled ? pow2_scale(row_stats[1]) : 1.f;
     if (threadIdx.x == 0) q_scale[b] = (metric == RL_METRIC_L2 ? 2.f : 1.f) / (scale * rs_e);
   }
   __half* img = qimg + (size_t)group * n_ks * kMaxQ * kSliceK;  // groups are laid out with the full 256-row pitch
@@ -1333,9 +1364,36 @@ int tcgen05_prepare_queries(const rl_scan_params* p, const float* q_inv_norm, fl
   const int n_ks = (p->d + kSliceK - 1) / kSliceK;
   RL_CUDA_CHECK(cudaMemsetAsync(qimg, 0, tcgen05_qimg_bytes(p->B, p->d), stream));
   query_image_kernel<<<p->B, 128, 0, stream>>>(p->Q, p->B, p->d, p->metric, q_inv_norm, p->row_stats, q_scale,
-                                                 reinterpret_cast<__half*>(qimg), n_ks);
+                                                 reinterpret_cast<__half*>(qimg), n_ks, p->e_dtype == 1 ? 0 : 1);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+typedef CUresult (*ScanEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ScanEncodeTiledFn scan_encode_tiled_fn() {
+  static ScanEncodeTiledFn fn = []() -> ScanEncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<ScanEncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// Tensor map over the fp16-stored corpus E[n_rows, ld] (d valid columns): box = 64 halves (one 128-byte swizzle row)
+// x 128 rows = exactly one UMMA A stage; rows past n_rows and columns past d read as zero.
+static bool make_corpus_tensor_map(CUtensorMap* tm, const void* E, int64_t n_rows, int64_t ld, int d) {
+  ScanEncodeTiledFn enc = scan_encode_tiled_fn();
+  if (enc == nullptr || (reinterpret_cast<uintptr_t>(E) & 15) != 0 || (ld * 2) % 16 != 0 || n_rows >= (int64_t(1) << 31)) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)kSliceK, (cuuint32_t)kTileM};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(E), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 constexpr int kMaxGroups = 4;   // query groups walked per corpus tile in one launch (B <= 1024 per launch)
@@ -1356,6 +1414,12 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     return v < 1 ? 1 : (v > kMaxGroups ? kMaxGroups : v);
   }();
   static const bool seq_mode = []() { const char* e = getenv("RL_TC_GROUPMODE"); return e != nullptr && e[0] == 's'; }();
+  // fp16 storage: the corpus tiles go HBM -> shared memory through a tensor map (TMA writes the swizzled UMMA tile,
+  // no loader warps, no registers in between).  RL_TC_TMA=0 keeps the register loaders (A/B).
+  CUtensorMap tmE;
+  memset(&tmE, 0, sizeof(tmE));
+  static const bool tma_env = []() { const char* e = getenv("RL_TC_TMA"); return e == nullptr || atoi(e) != 0; }();
+  const bool tma_rows = p->e_dtype == 1 && tma_env && make_corpus_tensor_map(&tmE, p->E, p->n_rows, p->ld, p->d);
   for (int g0 = 0; g0 < groups; g0 += max_groups) {
     TcArgs t;
     t.a = a_in;
@@ -1384,6 +1448,7 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
     t.n_ks = n_ks;
     static const int pf_pairs_env = []() { const char* e = getenv("RL_TC_PF_PAIRS"); return e ? atoi(e) : kPrefetchItems / 2; }();
     t.pf_pairs = pf_pairs_env < 0 ? 0 : (pf_pairs_env > 16 ? 16 : pf_pairs_env);
+    t.tma_rows = tma_rows ? 1 : 0;
     t.buf_cols = (t.nq + 31) / 32 * 32;
     int cols = 32;
     while (cols < 2 * t.buf_cols) cols *= 2;
@@ -1428,7 +1493,7 @@ int launch_scan_tcgen05(const ScanArgs& a_in, const rl_scan_params* p, const flo
       cfg.blockDim = dim3(kThreads);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = stream;
-      RL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, t));
+      RL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmE, t));
       return RL_OK;
     };
     int rc;
