@@ -339,6 +339,21 @@ def test_fp16_storage_matches_oracle(rl, metric):
     assert st["algo"] == 2
 
 
+@pytest.mark.parametrize("d,n_chunks,B", [(72, 700, 5), (96, 1500, 64), (104, 900, 7), (200, 2600, 256), (1024, 300, 33)])
+def test_fp16_storage_tensor_map_edges(rl, d, n_chunks, B):
+    """fp16 storage brings the corpus tiles through a TMA tensor map (box 64 halves x 128 rows): dimensions that
+    end inside a box (72, 96, 104, 200: the tail reads as zeros), a last tile with fewer than 128 rows, an odd number
+    of tiles (the second CTA of the last pair has none) and batches that leave the pair kernel (B < 64)."""
+    E, off = make_corpus(n_chunks, (1, 7), d, seed=500 + d, fp16_round=True)
+    Q = make_queries(E, B, seed=501 + d)
+    idx16 = rl.CorpusIndex(E, off, storage="fp16")
+    cfg = rl.RAGLiteConfig(reranker=None)
+    ids, sims, counts = rl.vector_search_batch(Q, num_results=8, config=cfg, index=idx16)
+    assert idx16.scan_stats()["algo"] == 2
+    for b in range(0, B, max(1, B // 12)):
+        check_sql_semantics(E, off, Q[b], ids[b, :counts[b]], sims[b, :counts[b]], k=8)
+
+
 def test_fp16_storage_rejects_lossy_input(rl):
     E, off = make_corpus(100, 2, 64, seed=83)          # general float32 values: not representable
     with pytest.raises(ValueError):
