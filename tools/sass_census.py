@@ -10,7 +10,7 @@ from collections import Counter, OrderedDict
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parents[1] / "raglite_b200" / "lib" / "libraglite_b200.so"
-OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "UBLKCP", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "HMMA", "LDG.E.128", "LDGSTS", "ATOMG", "REDG", "RED.E"]
+OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "UBLKCP", "UTMALDG", "UTMAPF", "UTMASTG", "UTCBAR", "SYNCS", "HMMA", "LDG.E.128", "LDGSTS", "ATOMG", "REDG", "RED.E"]
 
 sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()  # noqa: E731
@@ -43,5 +43,5 @@ for name, c in per.items():
     tot.update(c)
 print(f"| **all** | {tot['_total']} | " + " | ".join(str(tot[o]) for o in OPS) + " |")
 print("\nUTCHMMA = tcgen05.mma (fp16 kind), LDTM = tcgen05.ld, UBLKCP = cp.async.bulk (1-D, TMA engine), "
-      "UTMALDG = cp.async.bulk.tensor (tensor-map TMA), UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, "
+      "UTMALDG = cp.async.bulk.tensor (tensor-map TMA), UTMAPF = cp.async.bulk.prefetch.tensor, UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, "
       "HMMA = legacy mma.sync, LDGSTS = cp.async.")
