@@ -697,7 +697,13 @@ def main() -> None:  # noqa: PLR0915
                 "tensor_tflops": flops / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0,
                 "tensor_peak_tflops": tensor_peak,
                 "tensor_frac": (flops / (scan_ms * 1e-3) / 1e12 / tensor_peak) if (tensor_peak and scan_ms > 0) else None}
-    if B > 256 and tensor_peak:   # configs[2]: 2*B*d flop per 4*d bytes of corpus is past the ridge -> tensor pipe binds
+    # Which roof binds: the arithmetic intensity of the launch (2*B*d flop per row of esize*d bytes) against the ridge of
+    # the measured peaks.  fp32 corpus, B = 256: 128 flop/B, below the ridge (~229) -> HBM.  configs[2] (B = 1024) and the
+    # fp16 layout at B = 256 (256 flop/B; ncu: tensor pipe 81 % active at the power-capped clock) are past it -> tensor.
+    ridge = (tensor_peak * 1e12) / (hbm_peak * 1e9) if tensor_peak else None
+    roofline["flop_per_byte"] = flops / alg_bytes
+    roofline["ridge_flop_per_byte"] = ridge
+    if tensor_peak and flops / alg_bytes > ridge:
         roofline.update({"bound": "tensor", "achieved": roofline["tensor_tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": roofline["tensor_frac"], "hbm_gbs": achieved, "hbm_frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"})

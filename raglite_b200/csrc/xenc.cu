@@ -866,14 +866,39 @@ __global__ void __launch_bounds__(128, 5) attention_kernel(const __half* __restr
   }
 }
 
+// Sequence indices of a call sorted by length, longest first (counting sort over the lengths; equal lengths in any
+// order).  One CTA, once per forward.
+constexpr int kMaxSeqLenBins = 2048;
+__global__ void __launch_bounds__(1024) seq_order_kernel(const int32_t* __restrict__ cu, int P, int32_t* __restrict__ order) {
+  __shared__ int cnt[kMaxSeqLenBins + 1];
+  for (int i = threadIdx.x; i <= kMaxSeqLenBins; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&cnt[min(cu[i + 1] - cu[i], kMaxSeqLenBins)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {   // exclusive prefix from the longest bin down: cnt[L] becomes the first slot of length L
+    int run = 0;
+    for (int b = kMaxSeqLenBins; b >= 0; --b) { const int c = cnt[b]; cnt[b] = run; run += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) order[atomicAdd(&cnt[min(cu[i + 1] - cu[i], kMaxSeqLenBins)], 1)] = i;
+}
+
 // Two 16-query tiles per warp and key block: the K / V fragments are fetched from shared memory once and feed both
 // tiles' MMAs, and the two tiles' softmax chains (max -> ex2 -> sum -> pack) interleave.  ncu on the one-tile
 // kernel showed no saturated pipe (ex2 32 %, HMMA 30 %, issue 37 %) with three CTAs = 12 warps per SM: the
 // dependent chain of a single tile per warp, not a throughput limit, set the pace.
+//
+// Launch order: one CTA per (sequence, head), heads fastest, the sequences walked longest first (`order`, built once per call by
+// seq_order_kernel).  A CTA's work grows with L^2 and the lengths of a call spread over an order of magnitude; in
+// arrival order a long sequence that starts in the last wave leaves most SMs idle while it finishes.  Longest first
+// the last wave holds the shortest sequences.  The last key block is cut at a multiple of 16 keys (one PV k-step)
+// instead of 64: a 200-token sequence computes 208 keys, not 256.
 __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
-                                                         int H, int n_heads, float scale_log2e, __half* __restrict__ ctx) {
+                                                         const int32_t* __restrict__ order, int H, int n_heads,
+                                                         float scale_log2e, __half* __restrict__ ctx) {
   extern __shared__ __align__(16) unsigned char att_smem[];
-  const int seq = blockIdx.x, head = blockIdx.y;
+  const int head = (int)(blockIdx.x % (unsigned)n_heads), slot = (int)(blockIdx.x / (unsigned)n_heads);   // heads fastest
+  const int seq = order != nullptr ? order[slot] : slot;
   const int t0 = cu[seq], L = cu[seq + 1] - t0;
   const int Lp = (L + 63) / 64 * 64;
   __half* Ks = reinterpret_cast<__half*>(att_smem);
@@ -920,18 +945,27 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
 #pragma unroll
         for (int e = 0; e < 4; ++e) O[t][i][e] = 0.f;
     }
-    for (int kb = 0; kb < Lp; kb += 64) {
+    for (int kb = 0; kb < L; kb += 64) {
+      // k-steps of 16 keys in this block: 4, or fewer in the last block (warp-uniform; the loops stay unrolled)
+      const int nkk = L - kb >= 64 ? 4 : (L - kb + 15) >> 4;
       float S[2][8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        uint32_t b[4];
-        ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
+        if (j < 2 * nkk) {
+          uint32_t b[4];
+          ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+          for (int t = 0; t < 2; ++t) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) S[t][j][e] = 0.f;
-          mma16816(S[t][j], a[t][0], b[0], b[1]);
-          mma16816(S[t][j], a[t][1], b[2], b[3]);
+            for (int e = 0; e < 4; ++e) S[t][j][e] = 0.f;
+            mma16816(S[t][j], a[t][0], b[0], b[1]);
+            mma16816(S[t][j], a[t][1], b[2], b[3]);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) S[t][j][e] = -INFINITY;
         }
       }
       if (kb + 64 > L) {   // only the last key block holds padding keys
@@ -967,15 +1001,18 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j) {
+          if (j >= 2 * nkk) continue;   // key tiles past the cut: no MMA reads them
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float pexp = ex2_approx(fmaf(S[t][j][e], scale_log2e, e < 2 ? -mn[t][0] : -mn[t][1]));   // -inf -> 0
             S[t][j][e] = pexp;
             if (e < 2) l[t][0] += pexp; else l[t][1] += pexp;
           }
+        }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
+        if (kk >= nkk) continue;
         uint32_t pa[2][4];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -1202,7 +1239,8 @@ extern "C" size_t rl_xenc_workspace_bytes(const rl_xenc_weights* w, int T) {
   if (w == nullptr || T < 0) return 0;
   const size_t H = (size_t)w->hidden, F = (size_t)w->ffn;
   // hidden, qkv (3H), ctx, tmp (H), ffn (F) -- fp16 rows
-  return ((size_t)T * (H + 3 * H + H + H + F) * sizeof(__half) + 4096);
+  // + the length-sorted sequence order of the call (at most T sequences), 16-byte aligned behind the rows
+  return ((size_t)T * (H + 3 * H + H + H + F) * sizeof(__half) + (size_t)T * sizeof(int32_t) + 4096);
 }
 
 extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids, const int32_t* type_ids,
@@ -1225,6 +1263,15 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   __half* ctx = qkv + (size_t)T * 3 * H;
   __half* tmp = ctx + (size_t)T * H;
   __half* ffn = tmp + (size_t)T * H;
+  int32_t* seq_order = reinterpret_cast<int32_t*>(
+      (reinterpret_cast<uintptr_t>(ffn + (size_t)T * F) + 15) & ~uintptr_t(15));   // [P] (P <= T)
+  RL_REQUIRE(P <= T, RL_EINVAL, "rl_xenc_score: more sequences than tokens");
+  // Attention walks the sequences longest first (RL_XENC_ATT_LPT=0: in arrival order, the A/B baseline).
+  static const bool att_lpt = []() { const char* e = getenv("RL_XENC_ATT_LPT"); return e == nullptr || atoi(e) != 0; }();
+  if (att_lpt) {
+    seq_order_kernel<<<1, 1024, 0, stream>>>(cu_seqlens, P, seq_order);
+    RL_CUDA_CHECK(cudaGetLastError());
+  }
   const int tok_blocks = (T + 7) / 8;
   const bool ln_vec = H % 128 == 0;   // (LayerNorm gamma / beta come from torch allocations: 16-byte aligned)
   embed_ln_kernel<<<tok_blocks, 256, 0, stream>>>(input_ids, type_ids, pos_ids, reinterpret_cast<const __half*>(w->word_emb),
@@ -1252,7 +1299,8 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     if (rc != RL_OK) return rc;
     static const bool att2 = []() { const char* e = getenv("RL_XENC_ATT2"); return e == nullptr || atoi(e) != 0; }();
     auto attention = [&](size_t smem, int lo, int hi) {
-      if (att2 && lo == 0 && hi == max_len) attention2_kernel<<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx);
+      if (att2 && lo == 0 && hi == max_len)
+        attention2_kernel<<<dim3((unsigned)P * (unsigned)nh), 128, smem, stream>>>(qkv, cu_seqlens, att_lpt ? seq_order : nullptr, H, nh, scale, ctx);
       else if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
       else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
     };
