@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -891,8 +893,7 @@ __global__ void __launch_bounds__(1024) seq_order_kernel(const int32_t* __restri
 // Launch order: one CTA per (sequence, head), heads fastest, the sequences walked longest first (`order`, built once per call by
 // seq_order_kernel).  A CTA's work grows with L^2 and the lengths of a call spread over an order of magnitude; in
 // arrival order a long sequence that starts in the last wave leaves most SMs idle while it finishes.  Longest first
-// the last wave holds the shortest sequences.  The last key block is cut at a multiple of 16 keys (one PV k-step)
-// instead of 64: a 200-token sequence computes 208 keys, not 256.
+// the last wave holds the shortest sequences.  The last key block is 32 keys wide when no more than 32 are left.
 __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                          const int32_t* __restrict__ order, int H, int n_heads,
                                                          float scale_log2e, __half* __restrict__ ctx) {
@@ -945,34 +946,30 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
 #pragma unroll
         for (int e = 0; e < 4; ++e) O[t][i][e] = 0.f;
     }
-    for (int kb = 0; kb < L; kb += 64) {
-      // k-steps of 16 keys in this block: 4, or fewer in the last block (warp-uniform; the loops stay unrolled)
-      const int nkk = L - kb >= 64 ? 4 : (L - kb + 15) >> 4;
-      float S[2][8][4];
+    // One block of NKK k-steps (16 keys each) starting at key kb: NKK = 4 for a full 64-key block, 1..3 for the tail of
+    // the sequence.  NKK is a compile-time constant so that every loop unrolls without guards (run-time guards inside
+    // the unrolled body kept the compiler from interleaving the MMAs with the softmax: 134 -> 161 us per layer).
+    auto block = [&](auto nkk_tag, int kb) {
+      constexpr int NKK = decltype(nkk_tag)::value;
+      constexpr int NJ = 2 * NKK;   // 8-key score tiles
+      float S[2][NJ][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < 2 * nkk) {
-          uint32_t b[4];
-          ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
+      for (int j = 0; j < NJ; ++j) {
+        uint32_t b[4];
+        ldsm_x4(b, Ks + (size_t)(kb + j * 8 + (lane & 7)) * kAttPitch + (lane >> 3) * 8);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < 2; ++t) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) S[t][j][e] = 0.f;
-            mma16816(S[t][j], a[t][0], b[0], b[1]);
-            mma16816(S[t][j], a[t][1], b[2], b[3]);
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) S[t][j][e] = -INFINITY;
+          for (int e = 0; e < 4; ++e) S[t][j][e] = 0.f;
+          mma16816(S[t][j], a[t][0], b[0], b[1]);
+          mma16816(S[t][j], a[t][1], b[2], b[3]);
         }
       }
-      if (kb + 64 > L) {   // only the last key block holds padding keys
+      if (kb + NJ * 8 > L) {   // only the last key block holds padding keys
 #pragma unroll
         for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (kb + j * 8 + cp + (e & 1) >= L) S[t][j][e] = -INFINITY;
@@ -982,7 +979,7 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
       for (int t = 0; t < 2; ++t) {
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           mx0 = fmaxf(mx0, fmaxf(S[t][j][0], S[t][j][1]));
           mx1 = fmaxf(mx1, fmaxf(S[t][j][2], S[t][j][3]));
         }
@@ -990,6 +987,7 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // finite: every block holds at least one valid key (kb < L)
         mn[t][0] = fmaxf(m[t][0], mx0 * scale_log2e);
         mn[t][1] = fmaxf(m[t][1], mx1 * scale_log2e);
         const float c0 = ex2_approx(m[t][0] - mn[t][0]), c1 = ex2_approx(m[t][1] - mn[t][1]);
@@ -1001,18 +999,15 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j >= 2 * nkk) continue;   // key tiles past the cut: no MMA reads them
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float pexp = ex2_approx(fmaf(S[t][j][e], scale_log2e, e < 2 ? -mn[t][0] : -mn[t][1]));   // -inf -> 0
             S[t][j][e] = pexp;
             if (e < 2) l[t][0] += pexp; else l[t][1] += pexp;
           }
-        }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kk >= nkk) continue;
+      for (int kk = 0; kk < NKK; ++kk) {
         uint32_t pa[2][4];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -1033,7 +1028,12 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
           }
         }
       }
-    }
+    };
+    // 64-key blocks while more than 32 keys are left (the last of them may hold padding keys), then at most one
+    // 32-key block: a 200-token sequence computes 224 keys instead of 256 (L is warp-uniform).
+    int kb = 0;
+    for (; L - kb > 32; kb += 64) block(std::integral_constant<int, 4>{}, kb);
+    if (L - kb > 0) block(std::integral_constant<int, 2>{}, kb);
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       float l0 = l[t][0], l1 = l[t][1];
@@ -1053,36 +1053,42 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
 }
 
 // ---- pooler + classifier ----------------------------------------------------------------------------------
-// logit[s] = Wc . tanh(Wp h_s + bp) + bc with h_s the [CLS] row of sequence s.  A warp owns kClsSeqs
-// sequences (their [CLS] rows sit in shared memory as fp32) and walks the H pooler outputs; for one output
-// the lanes stride over the H inputs, so every Wp read is a coalesced 128-byte line shared by the warp's
-// sequences, followed by one warp-shuffle reduction per sequence.  (The first version read Wp row-per-lane:
-// 32 different lines per load instruction, 313 us per launch -- more than the rest of a small forward.)
-constexpr int kClsSeqs = 4;
-__global__ void __launch_bounds__(128) cls_head_kernel(const __half* __restrict__ hidden, const int32_t* __restrict__ cu,
-                                                       const float* __restrict__ Wp, const float* __restrict__ bp,
-                                                       const float* __restrict__ Wc, const float* __restrict__ bc, int P, int H,
-                                                       float* __restrict__ logit, float* __restrict__ score) {
-  extern __shared__ float cls_smem[];  // [warps][kClsSeqs][H]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int seq0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kClsSeqs;
-  if (seq0 >= P) return;
-  float* h = cls_smem + (size_t)warp * kClsSeqs * H;
+// logit[s] = Wc . tanh(Wp h_s + bp) + bc with h_s the [CLS] row of sequence s.  A CTA owns kClsSeqs sequences
+// (their [CLS] rows sit in shared memory as fp32) and its H/32 warps share the H pooler outputs; for one output
+// the lanes stride over the H inputs, so every Wp read is a coalesced 128-byte line shared by the CTA's
+// sequences, followed by one warp-shuffle reduction per sequence; the warps' partial logits meet in shared
+// memory and are summed in a fixed order.  (History: Wp row-per-lane, 32 lines per load instruction: 313 us per
+// launch; then one WARP per four sequences walking all H outputs one after the other: coalesced, but 16 CTAs of
+// serial work, 526 us per 256-sequence call = 9 % of the forward in the round-2 launch list.)
+constexpr int kClsSeqs = 2;
+constexpr int kClsMaxWarps = 16;
+__global__ void __launch_bounds__(kClsMaxWarps * 32) cls_head_kernel(const __half* __restrict__ hidden, const int32_t* __restrict__ cu,
+                                                                     const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                                     const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                                     int P, int H, float* __restrict__ logit,
+                                                                     float* __restrict__ score) {
+  extern __shared__ float cls_smem[];  // [kClsSeqs][H] [CLS] rows as fp32, then [warps][kClsSeqs] partial logits
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int seq0 = blockIdx.x * kClsSeqs;
+  float* h = cls_smem;
+  float* part = cls_smem + (size_t)kClsSeqs * H;
 #pragma unroll
   for (int s = 0; s < kClsSeqs; ++s) {
     const bool ok = seq0 + s < P;
     const __half* src = hidden + (size_t)cu[ok ? seq0 + s : seq0] * H;  // [CLS] token
-    for (int c = lane; c < H; c += 32) h[s * H + c] = ok ? __half2float(src[c]) : 0.f;
+    for (int c = threadIdx.x; c < H; c += blockDim.x) h[s * H + c] = ok ? __half2float(src[c]) : 0.f;
   }
-  __syncwarp();
+  __syncthreads();
   float out[kClsSeqs];
 #pragma unroll
   for (int s = 0; s < kClsSeqs; ++s) out[s] = 0.f;
-  for (int o = 0; o < H; ++o) {
+#pragma unroll 2
+  for (int o = warp; o < H; o += nw) {   // this warp's pooler outputs
     const float* w = Wp + (size_t)o * H;
     float a[kClsSeqs];
 #pragma unroll
     for (int s = 0; s < kClsSeqs; ++s) a[s] = 0.f;
+#pragma unroll 4
     for (int c = lane; c < H; c += 32) {
       const float wv = __ldg(w + c);
 #pragma unroll
@@ -1092,13 +1098,16 @@ __global__ void __launch_bounds__(128) cls_head_kernel(const __half* __restrict_
 #pragma unroll
     for (int s = 0; s < kClsSeqs; ++s) out[s] += tanhf(warp_sum_f(a[s]) + b) * wc;   // identical on every lane
   }
-  if (lane < kClsSeqs && seq0 + lane < P) {
-    float v = out[0];
+  if (lane == 0) {
 #pragma unroll
-    for (int s = 1; s < kClsSeqs; ++s) v = lane == s ? out[s] : v;
-    v += bc[0];
-    logit[seq0 + lane] = v;
-    score[seq0 + lane] = 1.f / (1.f + __expf(-v));  // FlashRank: sigmoid of the single logit
+    for (int s = 0; s < kClsSeqs; ++s) part[warp * kClsSeqs + s] = out[s];
+  }
+  __syncthreads();
+  if (threadIdx.x < kClsSeqs && seq0 + threadIdx.x < P) {   // fixed summation order: deterministic logits
+    float v = bc[0];
+    for (int wi = 0; wi < nw; ++wi) v += part[wi * kClsSeqs + threadIdx.x];
+    logit[seq0 + threadIdx.x] = v;
+    score[seq0 + threadIdx.x] = 1.f / (1.f + __expf(-v));  // FlashRank: sigmoid of the single logit
   }
 }
 
@@ -1328,7 +1337,8 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     else add_ln_kernel<false><<<tok_blocks, 256, 0, stream>>>(tmp, hidden, L.ln2_g, L.ln2_b, w->ln_eps, T, H, hidden);
     RL_CUDA_CHECK(cudaGetLastError());
   }
-  cls_head_kernel<<<(P + 4 * kClsSeqs - 1) / (4 * kClsSeqs), 128, (size_t)4 * kClsSeqs * H * sizeof(float), stream>>>(
+  const int cls_warps = H / 32 < kClsMaxWarps ? H / 32 : kClsMaxWarps;
+  cls_head_kernel<<<(P + kClsSeqs - 1) / kClsSeqs, cls_warps * 32, ((size_t)kClsSeqs * H + kClsMaxWarps * kClsSeqs) * sizeof(float), stream>>>(
       hidden, cu_seqlens, w->pooler_w, w->pooler_b, w->cls_w, w->cls_b, P, H, out_logit, out_score);
   RL_CUDA_CHECK(cudaGetLastError());
   return RL_OK;
