@@ -313,7 +313,7 @@ def run_rerank(args: argparse.Namespace, w: dict) -> None:
                 "dtype": "f16", "data": "synthetic (seeded weights, random token pairs, mean 200 tokens)",
                 "config": {"workload": w["desc"], "pairs": total, "tokens": tok, "parallelism": f"dp{world} over queries"},
                 "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": int(tok * 12 // world), "d2h_bytes_per_step": int(total * 8 // world)},
-                "gpu_launches": int(86 * np.ceil(tok / world / eng.max_tokens_per_call)), "reordered": int(order.shape[0])}
+                "gpu_launches": int(87 * np.ceil(tok / world / eng.max_tokens_per_call)), "reordered": int(order.shape[0])}
         # Tensor-pipe roofline of the whole forward (it is one fused sequence of GEMM-shaped kernels):
         # per layer 2*T*(4H^2 + 2HF) for the linears + 4*sum(L^2)*H for QK^T and PV.
         Hh, Ff, Ly = 384, 1536, 12
