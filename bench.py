@@ -77,6 +77,9 @@ def parse_args() -> argparse.Namespace:
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"],
                     help="clustered: tight clusters of near-duplicates + low-rank background, float16-rounded (tests/synth.py)")
     ap.add_argument("--check-queries", type=int, default=16, help="queries compared with the oracle after the timed region")
+    ap.add_argument("--burst-probe", action="store_true",
+                    help="after the timed loop: the same step launched after 250 ms of idle, six times (is the scan slower inside a "
+                         "loop of steps than timed alone?)")
     ap.add_argument("--filtered", action="store_true", help="also time metadata-filtered searches (both reference branches)")
     return ap.parse_args()
 
@@ -645,6 +648,16 @@ def main() -> None:  # noqa: PLR0915
     stats = local.scan_stats()
     n_rows = local.n_rows
     scan_ms = float(stage_ms["main_scan"])
+    burst = None
+    if args.burst_probe:   # the emit-mode launch timed alone: 250 ms of idle GPU before every step (CUDA events, as above)
+        alone = []
+        for _ in range(6):
+            torch.cuda.synchronize()
+            time.sleep(0.25)
+            device_step(flags=RL_FLAG_TIME_KERNELS)
+            alone.append(float(local.kernel_times_ms()["main_scan"]))
+        burst = {"main_scan_ms_after_250ms_idle": alone, "main_scan_ms_in_loop": scan_ms,
+                 "note": "same launch, same inputs; only the load before it differs"}
     comm_ms = None
     if world > 1:   # where does the multi-GPU step go: scan pipeline vs all-gather vs merge (CUDA events, this rank)
         from raglite_b200._index import merge_packed
@@ -812,6 +825,8 @@ def main() -> None:  # noqa: PLR0915
         }
         if filtered is not None:
             line["filtered"] = filtered
+        if burst is not None:
+            line["burst_probe"] = burst
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample_chunks or max(2048, min(w["chunks"], 16_384))
             r = cpu_reference_rate(w, sample, reps=3)
