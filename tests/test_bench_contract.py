@@ -48,3 +48,23 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert _run(["--gpus", "2"], {**base, "RANK": "1", "LOCAL_RANK": "1"}) == []
     lines = _run(["--gpus", "2"], {**base, "RANK": "0", "LOCAL_RANK": "0"})
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_carries_the_contract_keys():
+    """The GPU arm on configs[1] (1.2 GB corpus, seconds): one JSON line with roofline / e2e / clocks / launch count and
+    the oracle check of 16 queries green."""
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--workload", "c2", "--steps", "4", "--warmup", "3",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, check=True)
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    need = (REQUIRED - {"impl", "cpu_baseline"}) | {"roofline", "clocks", "gpu_launches", "check", "stage_ms"}
+    assert need <= set(d), need - set(d)
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and 0 < r["frac"] <= 1.0 and r["achieved"] > 0 and r["peak"] > 0 and "traffic" in r
+    assert d["gpu_launches"] > 0 and d["steps"] == 4 and d["n_gpus"] == 1
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert d["check"]["checked_queries"] >= 16 and d["check"]["identical_topk_sets"] == d["check"]["checked_queries"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
