@@ -896,9 +896,12 @@ __global__ void __launch_bounds__(1024) seq_order_kernel(const int32_t* __restri
 // the last wave holds the shortest sequences.  The last key block is 32 keys wide when no more than 32 are left.
 __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                          const int32_t* __restrict__ order, int H, int n_heads,
-                                                         float scale_log2e, __half* __restrict__ ctx) {
+                                                         float scale_log2e, __half* __restrict__ ctx, int n_seq, int seq_fastest) {
   extern __shared__ __align__(16) unsigned char att_smem[];
-  const int head = (int)(blockIdx.x % (unsigned)n_heads), slot = (int)(blockIdx.x / (unsigned)n_heads);   // heads fastest
+  // CTA -> (sequence slot, head): heads fastest (the twelve CTAs of a sequence run together and read the same qkv
+  // rows), or sequences fastest (RL_XENC_ATT_ORDER=1, the A/B alternative: every head walks the length-sorted list).
+  const int head = seq_fastest ? (int)(blockIdx.x / (unsigned)n_seq) : (int)(blockIdx.x % (unsigned)n_heads);
+  const int slot = seq_fastest ? (int)(blockIdx.x % (unsigned)n_seq) : (int)(blockIdx.x / (unsigned)n_heads);
   const int seq = order != nullptr ? order[slot] : slot;
   const int t0 = cu[seq], L = cu[seq + 1] - t0;
   const int Lp = (L + 63) / 64 * 64;
@@ -1277,6 +1280,7 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   RL_REQUIRE(P <= T, RL_EINVAL, "rl_xenc_score: more sequences than tokens");
   // Attention walks the sequences longest first (RL_XENC_ATT_LPT=0: in arrival order, the A/B baseline).
   static const bool att_lpt = []() { const char* e = getenv("RL_XENC_ATT_LPT"); return e == nullptr || atoi(e) != 0; }();
+  static const bool att_seq_fastest = []() { const char* e = getenv("RL_XENC_ATT_ORDER"); return e != nullptr && atoi(e) == 1; }();
   if (att_lpt) {
     seq_order_kernel<<<1, 1024, 0, stream>>>(cu_seqlens, P, seq_order);
     RL_CUDA_CHECK(cudaGetLastError());
@@ -1309,7 +1313,8 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     static const bool att2 = []() { const char* e = getenv("RL_XENC_ATT2"); return e == nullptr || atoi(e) != 0; }();
     auto attention = [&](size_t smem, int lo, int hi) {
       if (att2 && lo == 0 && hi == max_len)
-        attention2_kernel<<<dim3((unsigned)P * (unsigned)nh), 128, smem, stream>>>(qkv, cu_seqlens, att_lpt ? seq_order : nullptr, H, nh, scale, ctx);
+        attention2_kernel<<<dim3((unsigned)P * (unsigned)nh), 128, smem, stream>>>(qkv, cu_seqlens, att_lpt ? seq_order : nullptr, H, nh, scale, ctx,
+                                                                                       P, att_seq_fastest ? 1 : 0);
       else if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
       else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
     };
