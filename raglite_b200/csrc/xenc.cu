@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(1024) seq_order_kernel(const int32_t* __restri
 // the last wave holds the shortest sequences.  The last key block is 32 keys wide when no more than 32 are left.
 __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                          const int32_t* __restrict__ order, int H, int n_heads,
-                                                         float scale_log2e, __half* __restrict__ ctx, int n_seq, int seq_fastest) {
+                                                         float scale_log2e, __half* __restrict__ ctx, int n_seq, int seq_fastest, int stage_async) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   // CTA -> (sequence slot, head): heads fastest (the twelve CTAs of a sequence run together and read the same qkv
   // rows), or sequences fastest (RL_XENC_ATT_ORDER=1, the A/B alternative: every head walks the length-sorted list).
@@ -909,19 +909,32 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
   __half* Vs = Ks + (size_t)Lp * kAttPitch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t ld = (size_t)3 * H;
+  if (stage_async) {
+    // K / V of the head: global -> shared memory with cp.async (16 bytes each, zero-filled past the sequence), no
+    // registers in between; the first Q fragments are requested below while these copies are in flight.
 #pragma unroll 4
-  for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
-    const int j = idx >> 2, c = idx & 3;
-    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-    if (j < L) {
-      const __half* base = qkv + (size_t)(t0 + j) * ld + head * 32 + c * 8;
-      kv = __ldg(reinterpret_cast<const uint4*>(base + H));
-      vv = __ldg(reinterpret_cast<const uint4*>(base + 2 * H));
+    for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
+      const int j = idx >> 2, c = idx & 3;
+      const __half* base = qkv + (size_t)(t0 + (j < L ? j : L - 1)) * ld + head * 32 + c * 8;
+      const uint32_t nbytes = j < L ? 16u : 0u;
+      cp_async_16(smem_u32(Ks + (size_t)j * kAttPitch + c * 8), base + H, nbytes);
+      cp_async_16(smem_u32(Vs + (size_t)j * kAttPitch + c * 8), base + 2 * H, nbytes);
     }
-    *reinterpret_cast<uint4*>(Ks + (size_t)j * kAttPitch + c * 8) = kv;
-    *reinterpret_cast<uint4*>(Vs + (size_t)j * kAttPitch + c * 8) = vv;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < Lp * 4; idx += blockDim.x) {
+      const int j = idx >> 2, c = idx & 3;
+      uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+      if (j < L) {
+        const __half* base = qkv + (size_t)(t0 + j) * ld + head * 32 + c * 8;
+        kv = __ldg(reinterpret_cast<const uint4*>(base + H));
+        vv = __ldg(reinterpret_cast<const uint4*>(base + 2 * H));
+      }
+      *reinterpret_cast<uint4*>(Ks + (size_t)j * kAttPitch + c * 8) = kv;
+      *reinterpret_cast<uint4*>(Vs + (size_t)j * kAttPitch + c * 8) = vv;
+    }
   }
-  __syncthreads();
   const int r = lane >> 2, cp = (lane & 3) * 2;
   auto load_q = [&](int qb, uint32_t (&a)[2][4]) {   // A fragments of S = Q K^T for one 16-query tile (rows >= L read as zero)
     const int q0 = qb * 16 + r, q1 = q0 + 8;
@@ -935,10 +948,13 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
       a[ks][3] = q1 < L ? __ldg(reinterpret_cast<const uint32_t*>(p1 + 8)) : 0u;
     }
   };
+  // Q fragments of the warp's first pair of tiles: global loads that overlap the K / V staging above.
+  uint32_t a[2][2][4];
+  load_q(2 * warp, a[0]);
+  load_q(2 * warp + 1, a[1]);
+  if (stage_async) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   for (int pb = warp; pb * 32 < L; pb += 4) {   // this warp's pair of tiles: queries [32 pb, 32 pb + 32)
-    uint32_t a[2][2][4];
-    load_q(2 * pb, a[0]);
-    load_q(2 * pb + 1, a[1]);
     float m[2][2], l[2][2], O[2][4][4];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -1037,6 +1053,10 @@ __global__ void __launch_bounds__(128, 3) attention2_kernel(const __half* __rest
     int kb = 0;
     for (; L - kb > 32; kb += 64) block(std::integral_constant<int, 4>{}, kb);
     if (L - kb > 0) block(std::integral_constant<int, 2>{}, kb);
+    if ((pb + 4) * 32 < L) {   // the next pair's Q fragments travel while this pair's output is normalised and stored
+      load_q(2 * (pb + 4), a[0]);
+      load_q(2 * (pb + 4) + 1, a[1]);
+    }
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       float l0 = l[t][0], l1 = l[t][1];
@@ -1280,6 +1300,8 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
   RL_REQUIRE(P <= T, RL_EINVAL, "rl_xenc_score: more sequences than tokens");
   // Attention walks the sequences longest first (RL_XENC_ATT_LPT=0: in arrival order, the A/B baseline).
   static const bool att_lpt = []() { const char* e = getenv("RL_XENC_ATT_LPT"); return e == nullptr || atoi(e) != 0; }();
+  // K / V staging through cp.async with the first Q loads overlapped (RL_XENC_ATT_CPASYNC=0: plain loads, the A/B baseline)
+  static const bool att_stage_async = []() { const char* e = getenv("RL_XENC_ATT_CPASYNC"); return e == nullptr || atoi(e) != 0; }();
   static const bool att_seq_fastest = []() { const char* e = getenv("RL_XENC_ATT_ORDER"); return e != nullptr && atoi(e) == 1; }();
   if (att_lpt) {
     seq_order_kernel<<<1, 1024, 0, stream>>>(cu_seqlens, P, seq_order);
@@ -1314,7 +1336,7 @@ extern "C" int rl_xenc_score(const rl_xenc_weights* w, const int32_t* input_ids,
     auto attention = [&](size_t smem, int lo, int hi) {
       if (att2 && lo == 0 && hi == max_len)
         attention2_kernel<<<dim3((unsigned)P * (unsigned)nh), 128, smem, stream>>>(qkv, cu_seqlens, att_lpt ? seq_order : nullptr, H, nh, scale, ctx,
-                                                                                       P, att_seq_fastest ? 1 : 0);
+                                                                                       P, att_seq_fastest ? 1 : 0, att_stage_async ? 1 : 0);
       else if (att_quad) attention_kernel<true><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
       else attention_kernel<false><<<dim3(P, nh), 128, smem, stream>>>(qkv, cu_seqlens, H, nh, scale, ctx, lo, hi);
     };
